@@ -1,0 +1,291 @@
+// fa_fwd_sm100.cuh — FlashAttention-2 forward for sm_100a: TMA-fed K/V ring, tcgen05 MMAs with TMEM
+// accumulators, warp-specialised online softmax.
+//
+// Semantics follow the reference forward kernel (flash_attention_kernels.py:88-108, generalised with the
+// softmax scale and causal mask of flash_attention_openai_tutorial.py:50,160-161):
+//   S = Q K^T ; S2 = S * (scale*log2 e) ; mask j>i ; online max / exp2 / row-sum in fp32 ;
+//   P cast to the input dtype (RTNE) before P·V ; O = acc / l ; L = m + log2(l)  (log2 units, fp32).
+//
+// One CTA owns a 256-row query block as two 128-row tiles that ping-pong on the tensor core:
+//   warps 0-3  softmax for tile 0 (thread = one query row, `tcgen05.ld 32x32b`)
+//   warps 4-7  softmax for tile 1
+//   warp  8    TMA producer (Q once; K and V through an mbarrier ring)
+//   warp  9    MMA issuer (one elected thread) + TMEM owner
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).  P (16-bit) overwrites the first 64
+// columns of its S tile and is the TMEM A-operand of the P·V MMA; V is the MN-major shared-memory B operand.
+// The O rescale is lazy: a warp rewrites its O rows only when a row max grew by more than 2^8.
+#pragma once
+
+#include "sm100_ptx.cuh"
+
+namespace fa {
+
+struct FwdParams {
+  void* o;       // (B,H,N,D) 16-bit
+  float* lse;    // (B,H,N) fp32, log2 units
+  int B, H, N;
+  int64_t o_sB, o_sH, o_sN;  // element strides of O (last dim contiguous)
+  float scale_log2;          // softmax_scale * log2(e)
+  int q_blocks;              // ceil(N / 256)
+};
+
+template <int kD>
+struct FwdCfg {
+  static constexpr int kStages = (kD == 128) ? 2 : 4;
+  static constexpr int kTileBytes = 128 * kD * 2;  // one 128-row operand tile
+  static constexpr int kBoxBytes = 128 * 128;      // one 64-column box of it
+  static constexpr int kBoxes = kD / 64;
+  static constexpr int kSmemQ = 2 * kTileBytes;
+  static constexpr int kSmemKV = kStages * 2 * kTileBytes;
+  static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*alignment slack*/;
+  static constexpr int kThreads = 320;
+  static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kD;
+};
+
+template <bool kBf16, int kD, bool kCausal>
+__global__ void __launch_bounds__(320, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  using Cfg = FwdCfg<kD>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                  // [2][tile]
+  uint8_t* sK = smem + Cfg::kSmemQ;                    // [NS][tile]
+  uint8_t* sV = sK + NS * Cfg::kTileBytes;             // [NS][tile]
+
+  __shared__ uint64_t q_full[2], s_full[2], p_full[2], o_full[2];
+  __shared__ uint64_t k_full[NS], k_empty[NS], v_full[NS], v_empty[NS];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // heaviest (largest q index) blocks first so the causal triangle load-balances
+  const int qb = p.q_blocks - 1 - (int)blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * 256;
+  const int n_kv_total = (p.N + 127) >> 7;
+  const int ntiles = (p.N - q0 > 128) ? 2 : 1;
+  int nkv[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    int n = kCausal ? min(n_kv_total, ((q0 + 128 * t) >> 7) + 1) : n_kv_total;
+    nkv[t] = (t < ntiles) ? n : 0;
+  }
+  const int nkv_max = max(nkv[0], nkv[1]);
+
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_full[t], 1);
+    }
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 9) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_arrive_expect_tx(&q_full[t], Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(sQ + t * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmQ, &q_full[t], bx * 64, q0 + 128 * t, h,
+                      b);
+      }
+      for (int j = 0; j < nkv_max; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(sK + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &k_full[s], bx * 64, j * 128, h, b);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(sV + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &v_full[s], bx * 64, j * 128, h, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(kBf16, 128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(kBf16, 128, kD, 0, 1);
+      const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+      auto tS = [&](int t) { return tmem + (t ? Cfg::kTmemS1 : Cfg::kTmemS0); };
+      auto tO = [&](int t) { return tmem + (t ? Cfg::kTmemO1 : Cfg::kTmemO0); };
+
+      auto issue_s = [&](int t, int j) {
+        const int s = j % NS;
+        mbar_wait(&k_full[s], (j / NS) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          uint64_t da = umma_desc_kmajor(sQ_a + t * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes, k % 4);
+          uint64_t db = umma_desc_kmajor(sK_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes, k % 4);
+          umma_ss(tS(t), da, db, idesc_s, k > 0);
+        }
+        tc_commit(&s_full[t]);
+        // last tile that reads K block j releases the stage
+        const bool last_user = (t == 1) || (nkv[1] <= j);
+        if (last_user) tc_commit(&k_empty[s]);
+      };
+
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&q_full[t], 0);
+        issue_s(t, 0);
+      }
+      for (int j = 0; j < nkv_max; ++j) {
+        const int s = j % NS;
+        for (int t = 0; t < ntiles; ++t) {
+          if (j >= nkv[t]) continue;
+          mbar_wait(&p_full[t], j & 1);
+          mbar_wait(&v_full[s], (j / NS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint64_t db = umma_desc_mnmajor(sV_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, k);
+            umma_ts(tO(t), tS(t) + k * 8, db, idesc_o, (j > 0) || (k > 0));
+          }
+          tc_commit(&o_full[t]);
+          const bool last_user = (t == 1) || (nkv[1] <= j);
+          if (last_user) tc_commit(&v_empty[s]);
+          if (j + 1 < nkv[t]) issue_s(t, j + 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue (warps 0-7)
+    const int t = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + (t ? Cfg::kTmemS1 : Cfg::kTmemS0) + lane_base;
+    const uint32_t tO = tmem + (t ? Cfg::kTmemO1 : Cfg::kTmemO0) + lane_base;
+    const int my_nkv = nkv[t];
+    const int q_row = q0 + 128 * t + row;             // global query index
+    const float sl2 = p.scale_log2;
+
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < my_nkv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
+      tc_wait_ld();
+
+      const int kv0 = j * 128;
+      const bool diag = kCausal && (kv0 + 127 > q0 + 128 * t);   // block touches the diagonal
+      const bool ragged = (kv0 + 128 > p.N);
+      if (diag || ragged) {
+        int limit = p.N - kv0;                         // first invalid column (ragged)
+        if (kCausal) limit = min(limit, q_row - kv0 + 1);
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= limit) sr[c] = 0xff800000u;         // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2_approx((m_used - m_new) * sl2) : 1.0f;
+          if (need) m_used = m_new;
+          l *= alpha;
+          // O_t is stable once P·V of block j-1 has completed
+          mbar_wait(&o_full[t], (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < kD / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld_x32(tO + c * 32, orr);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+            tmem_st_x32(tO + c * 32, orr);
+          }
+        }
+      }
+      const float neg_ms = -m_used * sl2;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + 2 * i]), sl2, neg_ms));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + 2 * i + 1]), sl2, neg_ms));
+          l0 += p0;
+          l1 += p1;
+          pk[i] = pack2<kBf16>(p0, p1);
+        }
+        tmem_st_x16(tS + c * 16, pk);
+      }
+      l += l0 + l1;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    if (my_nkv > 0) {
+      mbar_wait(&o_full[t], (my_nkv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const bool in_range = q_row < p.N;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_sB + (int64_t)h * p.o_sH +
+                       (int64_t)q_row * p.o_sN;
+#pragma unroll
+      for (int c = 0; c < kD / 32; ++c) {
+        uint32_t orr[32];
+        tmem_ld_x32(tO + c * 32, orr);
+        tc_wait_ld();
+        if (in_range) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack2<kBf16>(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
+            v.y = pack2<kBf16>(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
+            v.z = pack2<kBf16>(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
+            v.w = pack2<kBf16>(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = v;
+          }
+        }
+      }
+      if (in_range) p.lse[((int64_t)b * p.H + h) * p.N + q_row] = m_used * sl2 + log2f(l);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace fa
