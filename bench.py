@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — attention fwd+bwd throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic input: forward, backward preprocess, dK/dV
+kernel, dQ kernel (4 launches of our kernels).  Workload at every N: BASELINE.json configs[2]
+(fwd+bwd bf16 B=2 H=32 N=8192 D=128 causal) PER GPU — head-sharded weak scaling: the job has 32*N heads and
+rank g owns heads [32g, 32g+32); no collective on the data path.
+
+`value`   whole-job algorithmic TFLOP/s (3.5 * 4*B*H*N^2*D*0.5 per step, flash_attention_openai_tutorial.py:630-636)
+          with inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks.
+`e2e`     the same metric through the public autograd API with HOST (pinned) buffers: H2D of Q, K, V, dO and D2H
+          of O, dQ, dK, dV inside the timed region.
+`roofline` tensor-core roofline of the dominant kernel (largest share of the step), timed alone with CUDA events.
+`cpu_baseline` the reference's CPU ground-truth path (torch SDPA + autograd.grad, src/test_correctness.py:33,48)
+          on the host cores, on a bounded head-subset of the same workload.
+`--impl reference` times that CPU path as the arm itself (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(B=2, H=32, N=8192, D=128, causal=True, dtype="bf16")
+WORKLOAD_NAME = "BASELINE configs[2]: fwd+bwd bf16 B=2 H=32 N=8192 D=128 causal, deterministic backward"
+METRIC = "attn fwd+bwd TFLOP/s (bf16, D=128, N=8k, causal)"
+
+
+def flops(B, H, N, D, causal, mode):
+    f = 4.0 * B * H * N * N * D * (0.5 if causal else 1.0)
+    return {"fwd": f, "bwd": 2.5 * f, "fwd_bwd": 3.5 * f}[mode]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_pass(heads: int, N: int, D: int, causal: bool, scale: float, seed: int = 42):
+    """One fwd+bwd of the reference's CPU ground-truth path on `heads` heads of the workload (fp32, as the
+    reference runs it).  Returns seconds."""
+    from oracle import attention_oracle as orc
+
+    g = torch.Generator().manual_seed(seed)
+    Q, K, V, dO = (torch.randn(1, heads, N, D, generator=g) for _ in range(4))
+    t0 = time.perf_counter()
+    orc.reference_sdpa_grads(Q, K, V, dO, scale, causal)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(budget_s: float = 12.0):
+    w = WORKLOAD
+    scale = 1.0 / w["D"] ** 0.5
+    heads = 2
+    cpu_reference_pass(1, 1024, w["D"], w["causal"], scale)  # warm the thread pool
+    done, spent = 0, 0.0
+    while spent < budget_s and done < w["B"] * w["H"]:
+        spent += cpu_reference_pass(heads, w["N"], w["D"], w["causal"], scale, seed=42 + done)
+        done += heads
+    tf = flops(1, done, w["N"], w["D"], w["causal"], "fwd_bwd") / spent / 1e12
+    return {"value": tf, "unit": "TFLOP/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{done} of {w['B'] * w['H']} heads of the workload (N={w['N']}, D={w['D']}, causal), fp32, "
+                      f"torch SDPA + autograd.grad exactly as src/test_correctness.py:33,48, {spent:.1f} s; "
+                      f"os.cpu_count()={os.cpu_count()}"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOAD
+    scale = 1.0 / w["D"] ** 0.5
+    heads = 2
+    for _ in range(args.warmup):
+        cpu_reference_pass(heads, w["N"], w["D"], w["causal"], scale)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_reference_pass(heads, w["N"], w["D"], w["causal"], scale, seed=42 + s)
+    dt = time.perf_counter() - t0
+    tf = flops(1, heads, w["N"], w["D"], w["causal"], "fwd_bwd") * args.steps / dt / 1e12
+    sample = (f"each step = {heads} of {w['B'] * w['H']} heads of the workload (N={w['N']}, D={w['D']}, causal), fp32, "
+              f"torch SDPA + autograd.grad as src/test_correctness.py:33,48; os.cpu_count()={os.cpu_count()}")
+    line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "per_gpu": True},
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": torch.get_num_threads(), "kind": "reference",
+                             "sample": sample},
+            "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from flash_attention_dlrs_b200 import FlashAttention, _lib, _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    w = WORKLOAD
+    B, H, N, D, causal = w["B"], w["H"], w["N"], w["D"], w["causal"]
+    scale = 1.0 / D ** 0.5
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(42 + rank)
+    host = [torch.randn(B, H, N, D, generator=g).to(dtype).pin_memory() for _ in range(4)]  # Q, K, V, dO
+    Q, K, V, dO = (t.to(dev, non_blocking=True) for t in host)
+    torch.cuda.synchronize()
+
+    def step():
+        O, L = _native.forward(Q, K, V, causal, scale)
+        return O, _native.backward(Q, K, V, O, dO, L, causal, scale)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_step = ms_total / args.steps
+    job_flops = flops(B, H * world, N, D, causal, "fwd_bwd")
+    value = job_flops / (ms_step * 1e-3) / 1e12
+
+    # ---- per-kernel timing (each kernel alone, CUDA events on the launching stream)
+    def time_fn(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    O, L = _native.forward(Q, K, V, causal, scale)
+    delta = _native.backward_preprocess(O, dO)
+    reps = max(args.steps, 5)
+    k_ms = {
+        "fwd": time_fn(lambda: _native.forward(Q, K, V, causal, scale), reps),
+        "bwd_preprocess": time_fn(lambda: _native.backward_preprocess(O, dO), reps),
+        "bwd_dkdv": time_fn(lambda: _native.backward(Q, K, V, O, dO, L, causal, scale, _native.BWD_DKDV, delta), reps),
+        "bwd_dq": time_fn(lambda: _native.backward(Q, K, V, O, dO, L, causal, scale, _native.BWD_DQ, delta), reps),
+    }
+    unit = flops(B, H, N, D, causal, "fwd") / 2.0  # one N x N x D matmul over the batch
+    # algorithmic matmuls per kernel: fwd S, PV; dK/dV kernel S, dP, dV, dK; dQ kernel dQ (its S / dP are recompute)
+    k_alg = {"fwd": 2 * unit, "bwd_dkdv": 4 * unit, "bwd_dq": 1 * unit}
+    k_hw = {"fwd": 2 * unit, "bwd_dkdv": 4 * unit, "bwd_dq": 3 * unit}
+    peaks = load_peaks()
+    dominant = max(("fwd", "bwd_dkdv", "bwd_dq"), key=lambda k: k_ms[k])
+    ach = k_alg[dominant] / (k_ms[dominant] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dominant, "achieved": ach, "peak": peaks["burst"], "unit": "TFLOP/s",
+                "frac": ach / peaks["burst"], "traffic": None,
+                "peak_source": peaks["source"] + ", burst bf16 (kernel timed alone)",
+                "hw_tflops_incl_recompute": k_hw[dominant] / (k_ms[dominant] * 1e-3) / 1e12}
+    pre_bytes = 2.0 * B * H * N * D * 2 + 4.0 * B * H * N
+    kernels = {k: {"ms": v} for k, v in k_ms.items()}
+    for k in ("fwd", "bwd_dkdv", "bwd_dq"):
+        kernels[k]["alg_tflops"] = k_alg[k] / (k_ms[k] * 1e-3) / 1e12
+        kernels[k]["hw_tflops"] = k_hw[k] / (k_ms[k] * 1e-3) / 1e12
+        kernels[k]["hw_frac_of_peak"] = kernels[k]["hw_tflops"] / peaks["burst"]
+    kernels["bwd_preprocess"]["gbs"] = pre_bytes / (k_ms["bwd_preprocess"] * 1e-3) / 1e9
+    kernels["bwd_preprocess"]["frac_of_hbm_peak"] = kernels["bwd_preprocess"]["gbs"] / peaks["hbm"]
+
+    # ---- end to end through the public autograd API with host buffers
+    out_host = [torch.empty(B, H, N, D, dtype=dtype).pin_memory() for _ in range(4)]  # O, dQ, dK, dV
+
+    def e2e_step():
+        q, k, v = (t.to(dev, non_blocking=True).requires_grad_(True) for t in host[:3])
+        do = host[3].to(dev, non_blocking=True)
+        o = FlashAttention.apply(q, k, v, causal, scale)
+        o.backward(do)
+        for dst, src in zip(out_host, (o.detach(), q.grad, k.grad, v.grad)):
+            dst.copy_(src, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e_steps = max(2, min(args.steps, 5))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e_steps):
+        e2e_step()
+    b.record()
+    barrier()
+    e_ms = a.elapsed_time(b) / e_steps
+    if world > 1:
+        t = torch.tensor([e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = t.item()
+    io_bytes = 4 * B * H * N * D * 2
+    e2e = {"value": job_flops / (e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e_ms,
+           "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
+           "api": "FlashAttention.apply(q, k, v, causal, scale) + O.backward(dO), pinned host buffers"}
+
+    if rank == 0:
+        cpu = cpu_baseline() if not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "per_gpu": True, "global_heads": H * world,
+                       "sharding": "heads, no data-path collective", "softmax_scale": scale,
+                       "l2": "inputs larger than L2 (Q,K,V,dO,O = 640 MiB per GPU vs 126 MB L2); no explicit flush",
+                       "flops": "algorithmic 3.5 * 4*B*H*N^2*D*0.5 (recompute in the two-kernel backward not counted)"},
+            "frac_of_bf16_peak": value / world / peaks["sustained"],
+            "frac_of_bf16_peak_note": "per-GPU value / sustained bf16 peak (" + peaks["source"] + ")",
+            "frac_of_bf16_burst_peak": value / world / peaks["burst"],
+            "fwd_tflops": kernels["fwd"]["alg_tflops"], "fwd_frac_of_bf16_burst_peak": kernels["fwd"]["alg_tflops"] / peaks["burst"],
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": 4 * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~12 s CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,135 @@
+"""Loader (and in-tree builder) of libfa_b200.so, the C-ABI library declared in include/fa_b200.h.
+
+The product path has no CPU or eager fallback: if the shared library is missing or a call fails, the
+error is raised to the caller (`FlashAttentionLibraryError`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libfa_b200.so"
+HEADER = REPO_ROOT / "include" / "fa_b200.h"
+
+FA_DTYPE_F16, FA_DTYPE_BF16, FA_DTYPE_F32 = 0, 1, 2
+
+# every symbol include/fa_b200.h declares
+EXPORTED_SYMBOLS = (
+    "fa_version",
+    "fa_last_error",
+    "fa_fwd",
+    "fa_bwd_preprocess",
+    "fa_bwd_workspace_bytes",
+    "fa_bwd",
+    "fa_bwd_partial",
+)
+
+
+class FlashAttentionLibraryError(RuntimeError):
+    """libfa_b200.so is missing, failed to load, or one of its entry points returned an error."""
+
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HEADER]
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    return any(s.stat().st_mtime > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/fa_api.cu for sm_100a into libfa_b200.so next to this file (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise FlashAttentionLibraryError("nvcc not found; cannot build libfa_b200.so")
+    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp), str(CSRC / "fa_api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise FlashAttentionLibraryError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+_lock = threading.Lock()
+_lib = None
+
+_I64x4 = ctypes.c_int64 * 4
+
+
+def _declare(lib):
+    vp, i, f, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+    st = ctypes.POINTER(ctypes.c_int64)
+    lib.fa_version.restype = i
+    lib.fa_version.argtypes = []
+    lib.fa_last_error.restype = ctypes.c_char_p
+    lib.fa_last_error.argtypes = []
+    lib.fa_fwd.restype = i
+    lib.fa_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, vp]
+    lib.fa_bwd_preprocess.restype = i
+    lib.fa_bwd_preprocess.argtypes = [vp, vp, vp, i, i, i, i, st, st, i, vp]
+    lib.fa_bwd_workspace_bytes.restype = sz
+    lib.fa_bwd_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.fa_bwd.restype = i
+    lib.fa_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i, vp]
+    lib.fa_bwd_partial.restype = i
+    lib.fa_bwd_partial.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i,
+                                   i, vp]
+
+
+def load():
+    """Return the ctypes handle of libfa_b200.so (loaded once per process).  Never builds implicitly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not LIB_PATH.exists():
+                raise FlashAttentionLibraryError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a). There is no CPU or eager fallback for the attention path."
+                )
+            try:
+                lib = ctypes.CDLL(str(LIB_PATH))
+            except OSError as e:  # pragma: no cover
+                raise FlashAttentionLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+            for sym in EXPORTED_SYMBOLS:
+                if not hasattr(lib, sym):
+                    raise FlashAttentionLibraryError(f"{LIB_PATH} does not export {sym}")
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def strides4(t) -> "ctypes.Array":
+    return _I64x4(*t.stride())
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().fa_last_error().decode("utf-8", "replace")
+        raise FlashAttentionLibraryError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,122 @@
+"""Torch-tensor front of the C ABI: allocation, stride hygiene, head-size padding, launches on torch's current stream.
+
+Mirrors what the reference's torch boundary does around its Triton launches (flash_attention_torch.py:38-74,
+96-154): pad the head size, allocate outputs with torch so the caching allocator owns every buffer, pass all
+four strides of every tensor.  Everything here runs on the GPU through libfa_b200.so; there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float16: _lib.FA_DTYPE_F16, torch.bfloat16: _lib.FA_DTYPE_BF16, torch.float32: _lib.FA_DTYPE_F32}
+MAX_HEAD_DIM = 128
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise TypeError(f"dtype {dtype} not supported.") from None
+
+
+def padded_head_dim(d: int, dtype: torch.dtype) -> int:
+    """Head size the kernels run at: 64 / 128 for 16-bit inputs, a power of two in [16, 128] for float32
+    (the reference pads to max(next_pow2(d), 16), flash_attention_torch.py:38)."""
+    if d < 1 or d > MAX_HEAD_DIM:
+        raise ValueError(f"head size d={d} not supported (1 <= d <= {MAX_HEAD_DIM})")
+    if dtype == torch.float32:
+        return max(1 << (d - 1).bit_length(), 16)
+    return 64 if d <= 64 else 128
+
+
+def _kernel_ready(t: torch.Tensor) -> torch.Tensor:
+    """A view the kernels can address: unit inner stride, 16-byte aligned base and outer strides."""
+    gran = 16 // t.element_size()
+    B, H, N, _ = t.shape
+    sB, sH, sN, sD = t.stride()
+    ok = sD == 1 and t.data_ptr() % 16 == 0 and sN % gran == 0
+    ok = ok and (H == 1 or sH % gran == 0) and (B == 1 or sB % gran == 0)
+    ok = ok and min(sB, sH, sN) >= 0
+    return t if ok else t.contiguous()
+
+
+def _pad_d(t: torch.Tensor, d_run: int) -> torch.Tensor:
+    d = t.shape[-1]
+    if d == d_run:
+        return t
+    return torch.nn.functional.pad(t, (0, d_run - d), mode="constant", value=0.0)
+
+
+def _stream_ptr(dev: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float):
+    """O (B,H,N,d) in the input dtype and L (B,H,N) float32 in log2 units.  Inputs already validated."""
+    lib = _lib.load()
+    B, H, N, d = Q.shape
+    code = dtype_code(Q.dtype)
+    d_run = padded_head_dim(d, Q.dtype)
+    q, k, v = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V))
+    O = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
+    L = torch.empty((B, H, N), dtype=torch.float32, device=Q.device)
+    with torch.cuda.device(Q.device):
+        rc = lib.fa_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(O), _ptr(L), B, H, N, d_run,
+                        _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(O),
+                        code, float(softmax_scale), int(bool(causal)), _stream_ptr(Q.device))
+    _lib.check(rc, "fa_fwd")
+    return (O if d_run == d else O[..., :d]), L
+
+
+def backward_preprocess(O: torch.Tensor, dO: torch.Tensor) -> torch.Tensor:
+    """delta (B,H,N) float32 = rowsum(O * dO).  O and dO must have the same (kernel-legal) head size."""
+    lib = _lib.load()
+    B, H, N, d = O.shape
+    code = dtype_code(O.dtype)
+    o, do = _kernel_ready(O), _kernel_ready(dO)
+    delta = torch.empty((B, H, N), dtype=torch.float32, device=O.device)
+    with torch.cuda.device(O.device):
+        rc = lib.fa_bwd_preprocess(_ptr(o), _ptr(do), _ptr(delta), B, H, N, d,
+                                   _lib.strides4(o), _lib.strides4(do), code, _stream_ptr(O.device))
+    _lib.check(rc, "fa_bwd_preprocess")
+    return delta
+
+
+BWD_DKDV, BWD_DQ = 1, 2
+
+
+def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int = BWD_DKDV | BWD_DQ, delta=None):
+    """dQ, dK, dV (B,H,N,d) in the input dtype; deterministic (bit-identical across runs).
+    `which` selects the dK/dV kernel, the dQ kernel or both (fa_bwd_partial); unselected outputs are uninitialised.
+    `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch."""
+    lib = _lib.load()
+    B, H, N, d = Q.shape
+    code = dtype_code(Q.dtype)
+    d_run = padded_head_dim(d, Q.dtype)
+    q, k, v, o, do = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V, O, dO))
+    lse = L.reshape(B, H, N).to(torch.float32).contiguous()
+    if delta is None:
+        delta = backward_preprocess(o, do)
+    dQ = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
+    dK = torch.empty_like(dQ)
+    dV = torch.empty_like(dQ)
+    ws_bytes = lib.fa_bwd_workspace_bytes(B, H, N, d_run, code)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=Q.device) if ws_bytes else None
+    with torch.cuda.device(Q.device):
+        rc = lib.fa_bwd_partial(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(lse), _ptr(delta), _ptr(dQ), _ptr(dK),
+                                _ptr(dV), _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, B, H, N,
+                                d_run, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),
+                                _lib.strides4(dQ), _lib.strides4(dK), _lib.strides4(dV),
+                                code, float(softmax_scale), int(bool(causal)), int(which), _stream_ptr(Q.device))
+    _lib.check(rc, "fa_bwd")
+    if d_run != d:
+        dQ, dK, dV = dQ[..., :d], dK[..., :d], dV[..., :d]
+    return dQ, dK, dV

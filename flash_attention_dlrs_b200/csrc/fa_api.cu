@@ -1,0 +1,314 @@
+// fa_api.cu — C ABI of libfa_b200.so (declared in include/fa_b200.h): argument checking, TMA tensor-map
+// encoding and kernel launches.  No torch types, no device allocation, no synchronisation.
+#include "../../include/fa_b200.h"
+
+#include "fa_bwd_sm100.cuh"
+#include "fa_fwd_sm100.cuh"
+#include "fa_preprocess.cuh"
+#include "fa_simt_f32.cuh"
+#include "tmap.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+int check_common(const char* fn, int B, int H, int N, int D, int dtype, float scale) {
+  if (B <= 0 || H <= 0 || N <= 0 || D <= 0) return fail(-1, "%s: B, H, N, D must be positive (got %d,%d,%d,%d)", fn, B, H, N, D);
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F32)
+    return fail(-2, "%s: dtype %d not supported (0 = f16, 1 = bf16, 2 = f32)", fn, dtype);
+  if (dtype == FA_DTYPE_F32) {
+    if (!(D == 16 || D == 32 || D == 64 || D == 128))
+      return fail(-3, "%s: float32 head size must be 16, 32, 64 or 128 (got %d); pad in the caller", fn, D);
+  } else if (!(D == 64 || D == 128)) {
+    return fail(-3, "%s: 16-bit head size must be 64 or 128 (got %d); pad in the caller", fn, D);
+  }
+  if (!(scale > 0.f) || !std::isfinite(scale)) return fail(-4, "%s: softmax_scale must be positive and finite", fn);
+  if (H > 65535 || B > 65535) return fail(-5, "%s: B and H must be <= 65535", fn);
+  return 0;
+}
+int check_tensor(const char* fn, const char* name, const void* p, const int64_t s[4], int dtype, int B, int H) {
+  if (!p) return fail(-6, "%s: %s is null", fn, name);
+  if (s[3] != 1) return fail(-7, "%s: %s last-dim stride must be 1 (got %lld)", fn, name, (long long)s[3]);
+  const int64_t gran = (dtype == FA_DTYPE_F32) ? 4 : 8;  // 16 bytes
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) return fail(-8, "%s: %s must be 16-byte aligned", fn, name);
+  if (s[2] % gran != 0 || (H > 1 && s[1] % gran != 0) || (B > 1 && s[0] % gran != 0))
+    return fail(-9, "%s: %s strides must be multiples of 16 bytes", fn, name);
+  return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  return 0;
+}
+
+void fill3(int64_t (&dst)[3], const int64_t s[4]) {
+  dst[0] = s[0], dst[1] = s[1], dst[2] = s[2];
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+template <bool kBf16, int kD, bool kCausal>
+int launch_fwd16(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p, int H,
+                 int B, cudaStream_t st) {
+  auto kern = fa::fa_fwd_kernel<kBf16, kD, kCausal>;
+  if (int r = set_smem(kern, fa::FwdCfg<kD>::kSmemBytes)) return r;
+  dim3 grid(p.q_blocks, H, B);
+  kern<<<grid, fa::FwdCfg<kD>::kThreads, fa::FwdCfg<kD>::kSmemBytes, st>>>(tq, tk, tv, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd launch");
+}
+
+template <int kD>
+int launch_fwd32(const fa::SimtParams& p, cudaStream_t st) {
+  auto kern = fa::fa_fwd_f32_kernel<kD>;
+  const int bytes = fa::SimtSmem<kD>::fwd_floats * 4;
+  if (int r = set_smem(kern, bytes)) return r;
+  dim3 grid((p.N + 63) / 64, p.H, p.B);
+  kern<<<grid, 256, bytes, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd(f32) launch");
+}
+
+template <int kD>
+int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
+  if (which & FA_BWD_DKDV) {
+    auto kern = fa::fa_bwd_dkdv_f32_kernel<kD>;
+    const int bytes = fa::SimtSmem<kD>::dkdv_floats * 4;
+    if (int r = set_smem(kern, bytes)) return r;
+    dim3 grid((p.N + 63) / 64, p.H, p.B);
+    kern<<<grid, 256, bytes, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(f32 dK/dV) launch");
+  }
+  if (which & FA_BWD_DQ) {
+    auto kern = fa::fa_bwd_dq_f32_kernel<kD>;
+    const int bytes = fa::SimtSmem<kD>::dq_floats * 4;
+    if (int r = set_smem(kern, bytes)) return r;
+    dim3 grid((p.N + 63) / 64, p.H, p.B);
+    kern<<<grid, 256, bytes, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(f32 dQ) launch");
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- backward (16-bit)
+template <bool kBf16, int kD, bool kCausal>
+int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaStream_t st) {
+  if (which & FA_BWD_DKDV) {
+    auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal>;
+    if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDkdv)) return r;
+    dim3 grid((p.N + 127) / 128, p.H, p.B);
+    kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDkdv, st>>>(m.q, m.k, m.v, m.dout, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(dK/dV) launch");
+  }
+  if (which & FA_BWD_DQ) {
+    auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal>;
+    if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDq)) return r;
+    dim3 grid((p.N + 127) / 128, p.H, p.B);
+    kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDq, st>>>(m.q, m.k, m.v, m.dout, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(dQ) launch");
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_version(void) { return 1; }
+
+const char* fa_last_error(void) { return g_err; }
+
+int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
+           const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+           const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
+  g_err[0] = 0;
+  if (int r = check_common("fa_fwd", B, H, N, D, dtype, softmax_scale)) return r;
+  if (!q_strides || !k_strides || !v_strides || !o_strides) return fail(-6, "fa_fwd: null stride array");
+  if (int r = check_tensor("fa_fwd", "q", q, q_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_fwd", "k", k, k_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_fwd", "v", v, v_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_fwd", "o", o, o_strides, dtype, B, H)) return r;
+  if (!lse) return fail(-6, "fa_fwd: lse is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (dtype == FA_DTYPE_F32) {
+    fa::SimtParams p{};
+    p.q = static_cast<const float*>(q), p.k = static_cast<const float*>(k), p.v = static_cast<const float*>(v);
+    p.out_o = static_cast<float*>(o), p.out_lse = lse;
+    p.B = B, p.H = H, p.N = N, p.D = D;
+    fill3(p.q_s, q_strides), fill3(p.k_s, k_strides), fill3(p.v_s, v_strides), fill3(p.o_s, o_strides);
+    p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
+    switch (D) {
+      case 16: return launch_fwd32<16>(p, st);
+      case 32: return launch_fwd32<32>(p, st);
+      case 64: return launch_fwd32<64>(p, st);
+      default: return launch_fwd32<128>(p, st);
+    }
+  }
+
+  const int bf = dtype == FA_DTYPE_BF16;
+  CUtensorMap tq, tk, tv;
+  if (int r = fa::make_tmap_bhnd_16bit(&tq, q, bf, B, H, N, D, q_strides[0], q_strides[1], q_strides[2], 128))
+    return fail(r, "fa_fwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
+  if (int r = fa::make_tmap_bhnd_16bit(&tk, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 128))
+    return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
+  if (int r = fa::make_tmap_bhnd_16bit(&tv, v, bf, B, H, N, D, v_strides[0], v_strides[1], v_strides[2], 128))
+    return fail(r, "fa_fwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
+  fa::FwdParams p{};
+  p.o = o, p.lse = lse, p.B = B, p.H = H, p.N = N;
+  p.o_sB = o_strides[0], p.o_sH = o_strides[1], p.o_sN = o_strides[2];
+  p.scale_log2 = softmax_scale * kLog2e;
+  p.q_blocks = (N + 255) / 256;
+#define FA_FWD_CASE(BF, DD, C) \
+  if (bf == BF && D == DD && (causal != 0) == C) return launch_fwd16<BF, DD, C>(tq, tk, tv, p, H, B, st);
+  FA_FWD_CASE(true, 128, true)
+  FA_FWD_CASE(true, 128, false)
+  FA_FWD_CASE(true, 64, true)
+  FA_FWD_CASE(true, 64, false)
+  FA_FWD_CASE(false, 128, true)
+  FA_FWD_CASE(false, 128, false)
+  FA_FWD_CASE(false, 64, true)
+  FA_FWD_CASE(false, 64, false)
+#undef FA_FWD_CASE
+  return fail(-3, "fa_fwd: no kernel for dtype %d D %d", dtype, D);
+}
+
+int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int H, int N, int D,
+                      const int64_t o_strides[4], const int64_t do_strides[4], int dtype, void* stream) {
+  g_err[0] = 0;
+  if (int r = check_common("fa_bwd_preprocess", B, H, N, D, dtype, 1.0f)) return r;
+  if (!o_strides || !do_strides) return fail(-6, "fa_bwd_preprocess: null stride array");
+  if (int r = check_tensor("fa_bwd_preprocess", "o", o, o_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd_preprocess", "dout", dout, do_strides, dtype, B, H)) return r;
+  if (!delta) return fail(-6, "fa_bwd_preprocess: delta is null");
+  fa::PreParams p{};
+  p.o = o, p.dout = dout, p.delta = delta, p.B = B, p.H = H, p.N = N, p.D = D;
+  p.o_sB = o_strides[0], p.o_sH = o_strides[1], p.o_sN = o_strides[2];
+  p.do_sB = do_strides[0], p.do_sH = do_strides[1], p.do_sN = do_strides[2];
+  p.total_rows = (long long)B * H * N;
+  const int vec = dtype == FA_DTYPE_F32 ? 4 : 8;
+  const int tpr = D / vec;
+  const long long rows_per_cta = (256 / tpr) * 4;
+  long long ctas = (p.total_rows + rows_per_cta - 1) / rows_per_cta;
+  if (ctas > 148 * 16) ctas = 148 * 16;  // grid-stride beyond 16 CTAs per SM
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define FA_PRE_CASE(E, T)                                                     \
+  if (dtype == E && tpr == T) {                                               \
+    fa::fa_bwd_preprocess_kernel<E, T><<<(unsigned)ctas, 256, 0, st>>>(p);    \
+    cudaError_t e = cudaGetLastError();                                       \
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fa_bwd_preprocess launch");   \
+  }
+  FA_PRE_CASE(0, 8) FA_PRE_CASE(0, 16) FA_PRE_CASE(1, 8) FA_PRE_CASE(1, 16)
+  FA_PRE_CASE(2, 4) FA_PRE_CASE(2, 8) FA_PRE_CASE(2, 16) FA_PRE_CASE(2, 32)
+#undef FA_PRE_CASE
+  return fail(-3, "fa_bwd_preprocess: no kernel for dtype %d D %d", dtype, D);
+}
+
+size_t fa_bwd_workspace_bytes(int B, int H, int N, int D, int dtype) {
+  (void)B, (void)H, (void)N, (void)D, (void)dtype;
+  return 0;  // the two-kernel backward needs no scratch: every gradient tile has a single owner CTA
+}
+
+int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+           void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int H, int N, int D,
+           const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+           const int64_t do_strides[4], const int64_t dq_strides[4], const int64_t dk_strides[4],
+           const int64_t dv_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
+  return fa_bwd_partial(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, D, q_strides,
+                        k_strides, v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale,
+                        causal, FA_BWD_DKDV | FA_BWD_DQ, stream);
+}
+
+int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                   const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+                   int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
+                   const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
+                   const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
+                   int causal, int which, void* stream) {
+  g_err[0] = 0;
+  if ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ)))
+    return fail(-10, "fa_bwd_partial: which must be a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
+  (void)workspace, (void)workspace_bytes;
+  if (int r = check_common("fa_bwd", B, H, N, D, dtype, softmax_scale)) return r;
+  if (!q_strides || !k_strides || !v_strides || !do_strides || !dq_strides || !dk_strides || !dv_strides)
+    return fail(-6, "fa_bwd: null stride array");
+  if (int r = check_tensor("fa_bwd", "q", q, q_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd", "k", k, k_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd", "v", v, v_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd", "dout", dout, do_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd", "dq", dq, dq_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd", "dk", dk, dk_strides, dtype, B, H)) return r;
+  if (int r = check_tensor("fa_bwd", "dv", dv, dv_strides, dtype, B, H)) return r;
+  if (!lse || !delta) return fail(-6, "fa_bwd: lse / delta is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (dtype == FA_DTYPE_F32) {
+    fa::SimtParams p{};
+    p.q = static_cast<const float*>(q), p.k = static_cast<const float*>(k), p.v = static_cast<const float*>(v);
+    p.dout = static_cast<const float*>(dout), p.lse = lse, p.delta = delta;
+    p.dq = static_cast<float*>(dq), p.dk = static_cast<float*>(dk), p.dv = static_cast<float*>(dv);
+    p.B = B, p.H = H, p.N = N, p.D = D;
+    fill3(p.q_s, q_strides), fill3(p.k_s, k_strides), fill3(p.v_s, v_strides), fill3(p.do_s, do_strides);
+    fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
+    p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
+    switch (D) {
+      case 16: return launch_bwd32<16>(p, which, st);
+      case 32: return launch_bwd32<32>(p, which, st);
+      case 64: return launch_bwd32<64>(p, which, st);
+      default: return launch_bwd32<128>(p, which, st);
+    }
+  }
+
+  const int bf = dtype == FA_DTYPE_BF16;
+  fa::BwdMaps m;
+  if (int r = fa::make_tmap_bhnd_16bit(&m.q, q, bf, B, H, N, D, q_strides[0], q_strides[1], q_strides[2], 128))
+    return fail(r, "fa_bwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
+  if (int r = fa::make_tmap_bhnd_16bit(&m.k, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 128))
+    return fail(r, "fa_bwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
+  if (int r = fa::make_tmap_bhnd_16bit(&m.v, v, bf, B, H, N, D, v_strides[0], v_strides[1], v_strides[2], 128))
+    return fail(r, "fa_bwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
+  if (int r = fa::make_tmap_bhnd_16bit(&m.dout, dout, bf, B, H, N, D, do_strides[0], do_strides[1], do_strides[2], 128))
+    return fail(r, "fa_bwd: cuTensorMapEncodeTiled(dout) failed (%d)", r);
+  fa::BwdParams p{};
+  p.lse = lse, p.delta = delta, p.dq = dq, p.dk = dk, p.dv = dv;
+  p.B = B, p.H = H, p.N = N;
+  fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
+  p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e;
+#define FA_BWD_CASE(BF, DD, C) \
+  if (bf == BF && D == DD && (causal != 0) == C) return launch_bwd16<BF, DD, C>(m, p, which, st);
+  FA_BWD_CASE(true, 128, true)
+  FA_BWD_CASE(true, 128, false)
+  FA_BWD_CASE(true, 64, true)
+  FA_BWD_CASE(true, 64, false)
+  FA_BWD_CASE(false, 128, true)
+  FA_BWD_CASE(false, 128, false)
+  FA_BWD_CASE(false, 64, true)
+  FA_BWD_CASE(false, 64, false)
+#undef FA_BWD_CASE
+  return fail(-3, "fa_bwd: no kernel for dtype %d D %d", dtype, D);
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// fa_bwd_sm100.cuh — deterministic FlashAttention-2 backward for sm_100a (16-bit inputs, fp32 accumulate).
+//
+// Math follows the reference backward (flash_attention_kernels.py:275-329, generalised with the softmax scale
+// and causal mask of flash_attention_openai_tutorial.py:239,292,389):
+//   P = exp2(S * scale*log2e - L) ; dV += P~^T dO ; dP = dO V^T ; dS = P o (dP - delta) ;
+//   dK += scale * dS~^T Q ; dQ += scale * dS~ K          (P~, dS~ rounded to the input dtype, RTNE)
+//
+// The reference accumulates dQ across key blocks through a global spin lock (flash_attention_kernels.py:305-320)
+// and is non-deterministic / broken (README.md:45-53).  Here every gradient tile has exactly one owner CTA and a
+// fixed accumulation order, so results are bit-identical run to run, with no atomics and no inter-CTA waiting:
+//   fa_bwd_dkdv_kernel : one CTA per 128-row key block j, loops over query blocks i, dK_j / dV_j live in TMEM;
+//   fa_bwd_dq_kernel   : one CTA per 128-row query block i, loops over key blocks j, dQ_i lives in TMEM
+//                        (S and dP are recomputed, precedent flash_attention_openai_tutorial.py:393-435).
+//
+// Both kernels share one structure.  Per (i, j) pair the two 128x128 "score" products are issued as two
+// 64-column halves; softmax warpgroup a (warps 0-3) owns half a, warpgroup b (warps 4-7) half b, thread = one
+// TMEM lane.  The elementwise results go back into TMEM as packed 16-bit A operands of the gradient MMAs, so the
+// only shared-memory traffic is TMA -> smem -> tensor core.  The MMA warp interleaves
+//   [grad a](t)  [score a](t+1)  [grad b](t)  [score b](t+1)
+// so the tensor core works on one half while the other half is in the elementwise stage.
+//
+//   warps 0-7  elementwise (P, dS) + epilogue      warp 8  TMA producer (+ row statistics)     warp 9  MMA issuer
+#pragma once
+
+#include "sm100_ptx.cuh"
+
+namespace fa {
+
+struct BwdMaps {
+  CUtensorMap q, k, v, dout;
+};
+
+struct BwdParams {
+  const float* lse;    // (B,H,N) log2 units
+  const float* delta;  // (B,H,N)
+  void *dq, *dk, *dv;  // (B,H,N,D) 16-bit
+  int B, H, N;
+  int64_t dq_s[3], dk_s[3], dv_s[3];  // {sB,sH,sN}
+  float scale, scale_log2;
+};
+
+template <int kD>
+struct BwdCfg {
+  static constexpr int kStages = 2;
+  static constexpr int kTileBytes = 128 * kD * 2;
+  static constexpr int kBoxBytes = 128 * 128;
+  static constexpr int kBoxes = kD / 64;
+  static constexpr int kStatBytes = 2 * 128 * 4;  // -lse and delta of one query block
+  static constexpr int kThreads = 320;
+  // stationary pair (2 tiles) + streamed pair ring (2 tiles per stage) + alignment slack
+  static constexpr int kSmemDkdv = 2 * kTileBytes + kStages * 2 * kTileBytes + kStages * kStatBytes + 1024;
+  static constexpr int kSmemDq = 2 * kTileBytes + kStages * 2 * kTileBytes + 1024;
+  // TMEM columns
+  static constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemAcc0 = 256, kTmemAcc1 = 256 + kD;
+};
+
+// TMEM accumulator rows -> 16-bit global rows: thread = one row, `ncols` fp32 columns starting at taddr.
+template <bool kBf16>
+__device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float mul, uint16_t* dst, bool in_range) {
+  for (int c = 0; c < ncols; c += 32) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr + c, r);
+    tc_wait_ld();
+    if (in_range) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 v;
+        v.x = pack2<kBf16>(__uint_as_float(r[8 * i + 0]) * mul, __uint_as_float(r[8 * i + 1]) * mul);
+        v.y = pack2<kBf16>(__uint_as_float(r[8 * i + 2]) * mul, __uint_as_float(r[8 * i + 3]) * mul);
+        v.z = pack2<kBf16>(__uint_as_float(r[8 * i + 4]) * mul, __uint_as_float(r[8 * i + 5]) * mul);
+        v.w = pack2<kBf16>(__uint_as_float(r[8 * i + 6]) * mul, __uint_as_float(r[8 * i + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + c + i * 8) = v;
+      }
+    }
+  }
+}
+
+// ================================================================================================ dK / dV
+template <bool kBf16, int kD, bool kCausal>
+__global__ void __launch_bounds__(320, 1)
+fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const BwdParams p) {
+  using Cfg = BwdCfg<kD>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                                   // stationary K_j
+  uint8_t* sV = sK + Cfg::kTileBytes;                   // stationary V_j
+  uint8_t* sQ = sV + Cfg::kTileBytes;                   // [NS] streamed Q_i
+  uint8_t* sDO = sQ + NS * Cfg::kTileBytes;             // [NS] streamed dO_i
+  float* sStat = reinterpret_cast<float*>(sDO + NS * Cfg::kTileBytes);  // [NS][2][128]: -lse, delta
+
+  __shared__ uint64_t kv_full, acc_full;
+  __shared__ uint64_t in_full[NS], stat_full[NS], in_empty[NS];
+  __shared__ uint64_t sc_full[2], p_full[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = jb * 128;
+  const int n_q_total = (p.N + 127) >> 7;
+  const int i_begin = kCausal ? jb : 0;
+  const int n_it = n_q_total - i_begin;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&kv_full, 1);
+    mbar_init(&acc_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&stat_full[s], 32);
+      mbar_init(&in_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sc_full[t], 1);
+      mbar_init(&p_full[t], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 9) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ producer: TMA + row statistics
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&kv_full, 2 * Cfg::kTileBytes);
+      for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
+        tma_load_4d(sK + bx * Cfg::kBoxBytes, &tmK, &kv_full, bx * 64, k0, h, b);
+        tma_load_4d(sV + bx * Cfg::kBoxBytes, &tmV, &kv_full, bx * 64, k0, h, b);
+      }
+    }
+    const float* lsep = p.lse + ((int64_t)b * p.H + h) * p.N;
+    const float* dlp = p.delta + ((int64_t)b * p.H + h) * p.N;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % NS;
+      const uint32_t ph = (it / NS) & 1;
+      const int q0 = (i_begin + it) * 128;
+      mbar_wait(&in_empty[s], ph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&in_full[s], 2 * Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
+          tma_load_4d(sQ + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmQ, &in_full[s], bx * 64, q0, h, b);
+          tma_load_4d(sDO + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmDO, &in_full[s], bx * 64, q0, h, b);
+        }
+      }
+      float* st = sStat + s * 256;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = lane * 4 + e;
+        const bool ok = q0 + r < p.N;
+        st[r] = ok ? -lsep[q0 + r] : -INFINITY;  // rows past N: P = exp2(-inf) = 0
+        st[128 + r] = ok ? dlp[q0 + r] : 0.f;
+      }
+      mbar_arrive(&stat_full[s]);
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_sc = umma_idesc_f16(kBf16, 128, 64, 0, 0);   // [128 kv] x [64 q], K = D
+      constexpr uint32_t idesc_gr = umma_idesc_f16(kBf16, 128, kD, 0, 1);   // [128 kv] x [D],   K = 64 q
+      const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO);
+
+      // S^T half = K_j Q_i[half]^T ; dP^T half = V_j dO_i[half]^T
+      auto issue_score = [&](int half, int s) {
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          uint64_t da = umma_desc_kmajor(sK_a + (k / 4) * Cfg::kBoxBytes, k % 4);
+          uint64_t db = umma_desc_kmajor(sQ_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
+          umma_ss(tmem + Cfg::kTmemS + half * 64, da, db, idesc_sc, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          uint64_t da = umma_desc_kmajor(sV_a + (k / 4) * Cfg::kBoxBytes, k % 4);
+          uint64_t db = umma_desc_kmajor(sDO_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
+          umma_ss(tmem + Cfg::kTmemDP + half * 64, da, db, idesc_sc, k > 0);
+        }
+        tc_commit(&sc_full[half]);
+      };
+      // dV += P^T[half] dO_i[half] ; dK += dS^T[half] Q_i[half]
+      auto issue_grad = [&](int half, int s, bool first) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t db = umma_desc_mnmajor(sDO_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, half * 4 + k);
+          umma_ts(tmem + Cfg::kTmemAcc0, tmem + Cfg::kTmemS + half * 64 + k * 8, db, idesc_gr, !(first && k == 0));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t db = umma_desc_mnmajor(sQ_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, half * 4 + k);
+          umma_ts(tmem + Cfg::kTmemAcc1, tmem + Cfg::kTmemDP + half * 64 + k * 8, db, idesc_gr, !(first && k == 0));
+        }
+      };
+
+      mbar_wait(&kv_full, 0);
+      mbar_wait(&in_full[0], 0);
+      tc_fence_after();
+      issue_score(0, 0);
+      issue_score(1, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % NS, sn = (it + 1) % NS;
+        const bool more = it + 1 < n_it;
+        mbar_wait(&p_full[0], it & 1);
+        tc_fence_after();
+        issue_grad(0, s, it == 0);
+        if (more) {
+          mbar_wait(&in_full[sn], ((it + 1) / NS) & 1);
+          tc_fence_after();
+          issue_score(0, sn);
+        }
+        mbar_wait(&p_full[1], it & 1);
+        tc_fence_after();
+        issue_grad(1, s, false);
+        tc_commit(&in_empty[s]);
+        if (more) issue_score(1, sn);
+      }
+      tc_commit(&acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ elementwise: P^T, dS^T  (warps 0-7)
+    const int half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;   // key row inside the block == TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + Cfg::kTmemS + half * 64 + lane_base;
+    const uint32_t tDP = tmem + Cfg::kTmemDP + half * 64 + lane_base;
+    const float sl2 = p.scale_log2;
+
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % NS;
+      const bool diag = kCausal && (it == 0);          // query block == key block
+      mbar_wait(&stat_full[s], (it / NS) & 1);
+      mbar_wait(&sc_full[half], it & 1);
+      tc_fence_after();
+      const float* st = sStat + s * 256 + half * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sr[32], dr[32];
+        tmem_ld_x32(tS + c * 32, sr);
+        tmem_ld_x32(tDP + c * 32, dr);
+        tc_wait_ld();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 nl = *reinterpret_cast<const float4*>(st + c * 32 + g * 4);
+          const float4 dl = *reinterpret_cast<const float4*>(st + 128 + c * 32 + g * 4);
+          const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
+          float pv[4], dv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = half * 64 + c * 32 + g * 4 + e;   // query row inside the block
+            float x = ex2_approx(fmaf(__uint_as_float(sr[g * 4 + e]), sl2, nlv[e]));
+            if (diag && row > col) x = 0.f;                  // causal: keep key <= query
+            pv[e] = x;
+            dv[e] = x * (__uint_as_float(dr[g * 4 + e]) - dlv[e]);
+          }
+          pp[g * 2] = pack2<kBf16>(pv[0], pv[1]);
+          pp[g * 2 + 1] = pack2<kBf16>(pv[2], pv[3]);
+          pd[g * 2] = pack2<kBf16>(dv[0], dv[1]);
+          pd[g * 2 + 1] = pack2<kBf16>(dv[2], dv[3]);
+        }
+        tmem_st_x16(tS + c * 16, pp);
+        tmem_st_x16(tDP + c * 16, pd);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[half]);
+    }
+
+    // epilogue: warpgroup a stores dV, warpgroup b stores scale * dK
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int kv_row = k0 + row;
+    const bool in_range = kv_row < p.N;
+    if (half == 0) {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(p.dv) + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)kv_row * p.dv_s[2];
+      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base, kD, 1.0f, dst, in_range);
+    } else {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(p.dk) + b * p.dk_s[0] + h * p.dk_s[1] + (int64_t)kv_row * p.dk_s[2];
+      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc1 + lane_base, kD, p.scale, dst, in_range);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+// ================================================================================================ dQ
+template <bool kBf16, int kD, bool kCausal>
+__global__ void __launch_bounds__(320, 1)
+fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                 const BwdParams p) {
+  using Cfg = BwdCfg<kD>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // stationary Q_i
+  uint8_t* sDO = sQ + Cfg::kTileBytes;                  // stationary dO_i
+  uint8_t* sK = sDO + Cfg::kTileBytes;                  // [NS] streamed K_j
+  uint8_t* sV = sK + NS * Cfg::kTileBytes;              // [NS] streamed V_j
+
+  __shared__ uint64_t qdo_full, acc_full;
+  __shared__ uint64_t in_full[NS], in_empty[NS];
+  __shared__ uint64_t sc_full[2], p_full[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blocks = (p.N + 127) >> 7;
+  const int ib = n_blocks - 1 - (int)blockIdx.x;        // heaviest (most key blocks) first under the causal mask
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = ib * 128;
+  const int n_it = kCausal ? ib + 1 : n_blocks;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&qdo_full, 1);
+    mbar_init(&acc_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sc_full[t], 1);
+      mbar_init(&p_full[t], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 9) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&qdo_full, 2 * Cfg::kTileBytes);
+      for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
+        tma_load_4d(sQ + bx * Cfg::kBoxBytes, &tmQ, &qdo_full, bx * 64, q0, h, b);
+        tma_load_4d(sDO + bx * Cfg::kBoxBytes, &tmDO, &qdo_full, bx * 64, q0, h, b);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % NS;
+        mbar_wait(&in_empty[s], ((it / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&in_full[s], 2 * Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
+          tma_load_4d(sK + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &in_full[s], bx * 64, it * 128, h, b);
+          tma_load_4d(sV + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &in_full[s], bx * 64, it * 128, h, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_sc = umma_idesc_f16(kBf16, 128, 64, 0, 0);   // [128 q] x [64 kv], K = D
+      constexpr uint32_t idesc_gr = umma_idesc_f16(kBf16, 128, kD, 0, 1);   // [128 q] x [D],    K = 64 kv
+      const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO);
+
+      // S half = Q_i K_j[half]^T ; dP half = dO_i V_j[half]^T
+      auto issue_score = [&](int half, int s) {
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          uint64_t da = umma_desc_kmajor(sQ_a + (k / 4) * Cfg::kBoxBytes, k % 4);
+          uint64_t db = umma_desc_kmajor(sK_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
+          umma_ss(tmem + Cfg::kTmemS + half * 64, da, db, idesc_sc, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          uint64_t da = umma_desc_kmajor(sDO_a + (k / 4) * Cfg::kBoxBytes, k % 4);
+          uint64_t db = umma_desc_kmajor(sV_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
+          umma_ss(tmem + Cfg::kTmemDP + half * 64, da, db, idesc_sc, k > 0);
+        }
+        tc_commit(&sc_full[half]);
+      };
+      // dQ += dS[half] K_j[half]
+      auto issue_grad = [&](int half, int s, bool first) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t db = umma_desc_mnmajor(sK_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, half * 4 + k);
+          umma_ts(tmem + Cfg::kTmemAcc0, tmem + Cfg::kTmemS + half * 64 + k * 8, db, idesc_gr, !(first && k == 0));
+        }
+      };
+
+      mbar_wait(&qdo_full, 0);
+      mbar_wait(&in_full[0], 0);
+      tc_fence_after();
+      issue_score(0, 0);
+      issue_score(1, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % NS, sn = (it + 1) % NS;
+        const bool more = it + 1 < n_it;
+        mbar_wait(&p_full[0], it & 1);
+        tc_fence_after();
+        issue_grad(0, s, it == 0);
+        if (more) {
+          mbar_wait(&in_full[sn], ((it + 1) / NS) & 1);
+          tc_fence_after();
+          issue_score(0, sn);
+        }
+        mbar_wait(&p_full[1], it & 1);
+        tc_fence_after();
+        issue_grad(1, s, false);
+        tc_commit(&in_empty[s]);
+        if (more) issue_score(1, sn);
+      }
+      tc_commit(&acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ elementwise: dS  (warps 0-7)
+    const int half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;   // query row inside the block == TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + Cfg::kTmemS + half * 64 + lane_base;
+    const uint32_t tDP = tmem + Cfg::kTmemDP + half * 64 + lane_base;
+    const float sl2 = p.scale_log2;
+    const int q_row = q0 + row;
+    const bool in_range = q_row < p.N;
+    const int64_t stat_idx = ((int64_t)b * p.H + h) * p.N + q_row;
+    const float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
+    const float dl = in_range ? p.delta[stat_idx] : 0.f;
+
+    for (int it = 0; it < n_it; ++it) {
+      const bool diag = kCausal && (it == n_it - 1);   // key block == query block
+      mbar_wait(&sc_full[half], it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sr[32], dr[32];
+        tmem_ld_x32(tS + c * 32, sr);
+        tmem_ld_x32(tDP + c * 32, dr);
+        tc_wait_ld();
+        uint32_t pd[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          float dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = half * 64 + c * 32 + g * 2 + e;   // key row inside the block
+            float x = ex2_approx(fmaf(__uint_as_float(sr[g * 2 + e]), sl2, neg_lse));
+            if (diag && col > row) x = 0.f;                  // causal: keep key <= query
+            dv[e] = x * (__uint_as_float(dr[g * 2 + e]) - dl);
+          }
+          pd[g] = pack2<kBf16>(dv[0], dv[1]);
+        }
+        tmem_st_x16(tS + c * 16, pd);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[half]);
+    }
+
+    // epilogue: each warpgroup stores half of the D columns of scale * dQ
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.dq) + b * p.dq_s[0] + h * p.dq_s[1] + (int64_t)q_row * p.dq_s[2] +
+                    half * (kD / 2);
+    store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base + half * (kD / 2), kD / 2, p.scale, dst, in_range);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace fa

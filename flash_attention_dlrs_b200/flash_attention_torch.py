@@ -1,0 +1,71 @@
+"""torch.autograd.Function boundary of the attention path — same names and argument meaning as the reference's
+flash_attention_torch.py (FlashAttention :21, FlashAttentionDeterministic :161, convert_triton_dtype :7).
+
+    O = FlashAttention.apply(Q, K, V)                       # reference call, scale = 1.0, non-causal
+    O = FlashAttention.apply(Q, K, V, causal, softmax_scale)  # added trailing arguments, order as in the
+                                                              # vendored tutorial (_attention.forward :441)
+
+Differences from the reference, all deliberate:
+  * the kernels are hand-written sm_100a CUDA reached through libfa_b200.so (no Triton, no autotune);
+  * the backward is deterministic, so FlashAttentionDeterministic is the same Function;
+  * L (base-2 logsumexp, flash_attention_kernels.py:106) is kept in float32 instead of the input dtype;
+  * bfloat16 is accepted, float64 / float8_e5m2 are not;
+  * head sizes that need padding also work in backward (the reference's padded backward is broken).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native
+
+MIN_TENSOR_SIZE = 16  # flash_attention_torch.py:5
+
+
+def convert_triton_dtype(torch_dtype):
+    """dtype whitelist with the reference's error (flash_attention_torch.py:7-18); returns the C-ABI dtype code."""
+    return _native.dtype_code(torch_dtype)
+
+
+def _validate(Q, K, V):
+    dev = Q.device
+    if dev.type != "cuda" or dev != K.device or dev != V.device:
+        raise NotImplementedError("Q, K, V must be on the same CUDA device")
+    if Q.dim() != 4 or Q.shape != K.shape or Q.shape != V.shape:
+        raise ValueError("Q, K, V must all be of shape (B, H, N, d)")
+    if Q.dtype != K.dtype or K.dtype != V.dtype:
+        raise ValueError("Q, K, V must have same dtype")
+    convert_triton_dtype(Q.dtype)
+
+
+class FlashAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool = False,
+                softmax_scale: float = 1.0) -> torch.Tensor:
+        _validate(Q, K, V)
+        causal = bool(causal)
+        softmax_scale = float(softmax_scale)
+        O, L = _native.forward(Q.detach(), K.detach(), V.detach(), causal, softmax_scale)
+        # same saved set as the reference (flash_attention_torch.py:77), unpadded
+        ctx.save_for_backward(Q, K, V, O, L)
+        ctx.causal = causal
+        ctx.softmax_scale = softmax_scale
+        return O
+
+    @staticmethod
+    def backward(ctx, grad_outputs, *args):
+        Q, K, V, O, L = ctx.saved_tensors
+        dO = grad_outputs
+        if Q.dtype != dO.dtype:
+            raise ValueError("dO must have same dtype as inputs")
+        dQ, dK, dV = _native.backward(Q, K, V, O, dO, L, ctx.causal, ctx.softmax_scale)
+        return dQ, dK, dV, None, None
+
+
+# The reference's second Function differs only in which (broken) backward kernel it launches
+# (flash_attention_torch.py:247,274); the backward here is always deterministic.
+FlashAttentionDeterministic = FlashAttention
+
+
+def flash_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0) -> torch.Tensor:
+    """Keyword-friendly front of FlashAttention.apply."""
+    return FlashAttention.apply(Q, K, V, causal, softmax_scale)

@@ -1,0 +1,62 @@
+"""Head-sharded multi-GPU attention: one process per GPU, every (batch, head) pair is an independent problem
+(the reference's grid axes 1, 2 are B and H, flash_attention_torch.py:59), so rank g owns a contiguous head
+slice and the compute path has no collective.  The only communication is the optional all-gather (NCCL over
+NVLink / NVSwitch via torch.distributed) that reassembles O on every rank when the caller asks for it.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def head_range(H: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous head slice [h0, h1) of rank `rank`; the first H % world ranks take one extra head."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(H, world)
+    h0 = rank * base + min(rank, rem)
+    return h0, h0 + base + (1 if rank < rem else 0)
+
+
+def all_gather_heads(local: torch.Tensor, H: int, group=None) -> torch.Tensor:
+    """(B, h_local, N, d) on each rank -> (B, H, N, d) on every rank, heads in rank order."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    B, _, N, d = local.shape
+    sizes = [head_range(H, r, world) for r in range(world)]
+    out = torch.empty((B, H, N, d), dtype=local.dtype, device=local.device)
+    if B == 1 and H % world == 0:
+        # each rank's slab is contiguous in the result: gather straight into it, no staging
+        dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+        return out
+    # general case (B > 1 or uneven slices): equal-sized staging slabs, then one strided copy per rank
+    h_max = max(h1 - h0 for h0, h1 in sizes)
+    slab = torch.zeros((B, h_max, N, d), dtype=local.dtype, device=local.device)
+    slab[:, : local.shape[1]] = local
+    stage = torch.empty((world, B, h_max, N, d), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(stage.view(-1), slab.view(-1), group=group)
+    for r, (h0, h1) in enumerate(sizes):
+        out[:, h0:h1] = stage[r, :, : h1 - h0]
+    assert sizes[rank][1] - sizes[rank][0] == local.shape[1]
+    return out
+
+
+def head_sharded_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0, group=None,
+                           gather: bool = False, attn_fn=None):
+    """Attention over this rank's head slice of replicated (B, H, N, d) inputs.
+
+    Returns the local (B, h_local, N, d) output, or the full (B, H, N, d) output on every rank when
+    `gather=True`.  The head slice is a strided view (no copy); `attn_fn(q, k, v, causal, softmax_scale)`
+    defaults to FlashAttention.apply.
+    """
+    if attn_fn is None:
+        from .flash_attention_torch import FlashAttention
+        attn_fn = FlashAttention.apply
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    H = Q.shape[1]
+    h0, h1 = head_range(H, rank, world)
+    o_local = attn_fn(Q[:, h0:h1], K[:, h0:h1], V[:, h0:h1], causal, softmax_scale)
+    if not gather or world == 1:
+        return o_local
+    return all_gather_heads(o_local.detach(), H, group)

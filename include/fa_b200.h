@@ -1,0 +1,80 @@
+/* fa_b200.h — C ABI of the B200-native FlashAttention-2 hot path (libfa_b200.so).
+ *
+ * Drop-in boundary for the attention path of 17ex/flash_attention_dlrs.  Each entry point replaces one
+ * Triton kernel launch the reference's torch boundary performs; the reference call site it stands in for is
+ * cited beside it (paths relative to the reference's src/).
+ *
+ * Conventions
+ *   - Tensors are (B, H, N, D) with ELEMENT strides {sB, sH, sN, sD}; sD must be 1.  For 16-bit dtypes the
+ *     other strides must be multiples of 8 elements and base pointers 16-byte aligned (TMA requirement).
+ *   - dtype: 0 = float16, 1 = bfloat16, 2 = float32.   D in {64, 128} for 16-bit, D % 4 == 0 and D <= 128 for
+ *     float32 (the Python boundary pads other head sizes, as flash_attention_torch.py:38-47 does).
+ *   - lse / delta are contiguous fp32 (B, H, N); lse is in LOG2 units: lse = log2(e) * logsumexp_j(scale*S_ij)
+ *     (flash_attention_kernels.py:106).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t), never synchronises, allocates nothing on the
+ *     device and keeps no pointer after returning.  The caller owns all buffers.
+ *   - Return value: 0 = OK, < 0 = argument / unsupported-shape error, > 0 = cudaError_t.  A description of the
+ *     last error on the calling thread is available from fa_last_error().
+ *   - Thread safe and re-entrant; CUDA-graph capturable.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_DTYPE_F16 0
+#define FA_DTYPE_BF16 1
+#define FA_DTYPE_F32 2
+
+/* ABI version of this header (bumped on any signature change). */
+int fa_version(void);
+
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char* fa_last_error(void);
+
+/* Forward pass: O = softmax(scale * Q K^T [+ causal mask]) V and lse.
+ * Replaces fwd_kernel[grid](...) at flash_attention_torch.py:61-74 and flash_attention_wrappers.py:46-61. */
+int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
+           const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+           const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream);
+
+/* Backward preprocess: delta[b,h,i] = sum_d O[b,h,i,d] * dO[b,h,i,d]  (fp32 accumulate).
+ * Replaces bwd_D_kernel[grid](...) at flash_attention_torch.py:125-133 and flash_attention_wrappers.py:110-118. */
+int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int H, int N, int D,
+                      const int64_t o_strides[4], const int64_t do_strides[4], int dtype, void* stream);
+
+/* Bytes of scratch fa_bwd needs for this problem (may be 0). */
+size_t fa_bwd_workspace_bytes(int B, int H, int N, int D, int dtype);
+
+/* Backward pass: dQ, dK, dV from Q, K, V, dO, lse, delta.  Deterministic: bit-identical across runs.
+ * Replaces bwd_kernel / bwd_deterministic_kernel launches at flash_attention_torch.py:136-154,274-292 and
+ * flash_attention_wrappers.py:122-174. */
+int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+           void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int H, int N, int D,
+           const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+           const int64_t do_strides[4], const int64_t dq_strides[4], const int64_t dk_strides[4],
+           const int64_t dv_strides[4], int dtype, float softmax_scale, int causal, void* stream);
+
+/* One half of fa_bwd at a time: `which` = FA_BWD_DKDV (the dK/dV kernel, owner = key block), FA_BWD_DQ (the dQ
+ * kernel, owner = query block) or both.  The reference has a single backward launch (flash_attention_torch.py:136-154)
+ * whose dQ part is the spin-locked read-modify-write of flash_attention_kernels.py:305-320; here the two parts are
+ * separate kernels, exposed for callers that need only some gradients and for per-kernel timing.  Outputs not
+ * selected are left untouched (their pointers must still be valid). */
+#define FA_BWD_DKDV 1
+#define FA_BWD_DQ 2
+int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                   const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+                   int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
+                   const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
+                   const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
+                   int causal, int which, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */

