@@ -5,6 +5,8 @@
 // softmax scale and causal mask of flash_attention_openai_tutorial.py:50,160-161):
 //   S = Q K^T ; S2 = S * (scale*log2 e) ; mask j>i ; online max / exp2 / row-sum in fp32 ;
 //   P cast to the input dtype (RTNE) before P·V ; O = acc / l ; L = m + log2(l)  (log2 units, fp32).
+// (An fp16 P against bf16 V would cut the P rounding error 8x, but tcgen05.mma kind::f16 with A = f16, B = bf16
+// raises an illegal-instruction fault on B200 — measured — so P follows the input dtype like the reference.)
 //
 // One CTA owns a 256-row query block as two 128-row tiles that ping-pong on the tensor core:
 //   warps 0-3  softmax for tile 0 (thread = one query row, `tcgen05.ld 32x32b`)

@@ -197,11 +197,16 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t box0_addr, uint32
 // Instruction descriptor for kind::f16 (fp16/bf16 inputs, fp32 accumulate).
 //   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major  [16] B major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int is_bf16, int M, int N, int a_mn_major,
-                                                     int b_mn_major) {
-  return (1u << 4) | (static_cast<uint32_t>(is_bf16) << 7) | (static_cast<uint32_t>(is_bf16) << 10) |
+// A and B formats are separate fields, but mixing f16 with bf16 faults on B200 (illegal instruction): keep them equal.
+__host__ __device__ constexpr uint32_t umma_idesc_f16_ab(int a_bf16, int b_bf16, int M, int N, int a_mn_major,
+                                                        int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(a_bf16) << 7) | (static_cast<uint32_t>(b_bf16) << 10) |
          (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int is_bf16, int M, int N, int a_mn_major,
+                                                     int b_mn_major) {
+  return umma_idesc_f16_ab(is_bf16, is_bf16, M, N, a_mn_major, b_mn_major);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]     (single thread issues)
