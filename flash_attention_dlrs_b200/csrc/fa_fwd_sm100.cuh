@@ -13,6 +13,8 @@
 //   warps 4-7  softmax for tile 1
 //   warp  8    TMA producer (Q once; K and V through an mbarrier ring)
 //   warp  9    MMA issuer (one elected thread) + TMEM owner
+//   warps 10-11 idle: they complete the third warpgroup so that `setmaxnreg` can move its registers to the
+//              softmax warpgroups (224 registers per softmax thread, no spills; 48 for the third warpgroup)
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).  P (16-bit) overwrites the first 64
 // columns of its S tile and is the TMEM A-operand of the P·V MMA; V is the MN-major shared-memory B operand.
 // The O rescale is lazy: a warp rewrites its O rows only when a row max grew by more than 2^8.
@@ -40,12 +42,12 @@ struct FwdCfg {
   static constexpr int kSmemQ = 2 * kTileBytes;
   static constexpr int kSmemKV = kStages * 2 * kTileBytes;
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*alignment slack*/;
-  static constexpr int kThreads = 320;
+  static constexpr int kThreads = 384;
   static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kD;
 };
 
 template <bool kBf16, int kD, bool kCausal>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<kD>;
@@ -56,7 +58,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* sK = smem + Cfg::kSmemQ;                    // [NS][tile]
   uint8_t* sV = sK + NS * Cfg::kTileBytes;             // [NS][tile]
 
-  __shared__ uint64_t q_full[2], s_full[2], p_full[2], o_full[2];
+  __shared__ uint64_t q_full[2], s_full[2], p_full[2][2], o_full[2];
   __shared__ uint64_t k_full[NS], k_empty[NS], v_full[NS], v_empty[NS];
   __shared__ uint32_t tmem_base_s;
 
@@ -81,7 +83,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1);
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t][0], 128);
+      mbar_init(&p_full[t][1], 128);
       mbar_init(&o_full[t], 1);
     }
     for (int s = 0; s < NS; ++s) {
@@ -103,6 +106,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  if (warp >= 8) {
+  setmaxnreg_dec<72>();   // third warpgroup: producer, MMA issuer, two idle warps
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
@@ -159,13 +164,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int s = j % NS;
         for (int t = 0; t < ntiles; ++t) {
           if (j >= nkv[t]) continue;
-          mbar_wait(&p_full[t], j & 1);
           mbar_wait(&v_full[s], (j / NS) & 1);
-          tc_fence_after();
+          // P arrives in two 64-key halves so the first half of P·V overlaps the second half of the exponentials
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            uint64_t db = umma_desc_mnmajor(sV_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, k);
-            umma_ts(tO(t), tS(t) + k * 8, db, idesc_o, (j > 0) || (k > 0));
+          for (int hf = 0; hf < 2; ++hf) {
+            mbar_wait(&p_full[t][hf], j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = hf * 4; k < hf * 4 + 4; ++k) {
+              uint64_t db = umma_desc_mnmajor(sV_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, k);
+              umma_ts(tO(t), tS(t) + k * 8, db, idesc_o, (j > 0) || (k > 0));
+            }
           }
           tc_commit(&o_full[t]);
           const bool last_user = (t == 1) || (nkv[1] <= j);
@@ -175,7 +184,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     }
     __syncwarp();
+  }
   } else {
+    setmaxnreg_inc<216>();
     // ------------------------------------------------------------------ softmax + epilogue (warps 0-7)
     const int t = warp >> 2;
     const int row = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
@@ -237,24 +248,34 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
       const float neg_ms = -m_used * sl2;
-      float l0 = 0.f, l1 = 0.f;
+      const uint64_t sl2_2 = f32x2_pack(sl2, sl2), nm2 = f32x2_pack(neg_ms, neg_ms);
+      uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};   // four packed partial row sums (8 fp32 chains)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + 2 * i]), sl2, neg_ms));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + 2 * i + 1]), sl2, neg_ms));
-          l0 += p0;
-          l1 += p1;
+          const uint64_t x2 = f32x2_fma(f32x2_pack_bits(sr[c * 32 + 2 * i], sr[c * 32 + 2 * i + 1]), sl2_2, nm2);
+          float x0, x1;
+          f32x2_unpack(x2, x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));
           pk[i] = pack2<kBf16>(p0, p1);
         }
         tmem_st_x16(tS + c * 16, pk);
+        if (c == 1) {
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_full[t][0]);
+        }
       }
-      l += l0 + l1;
+      float la, lb, lc, ld;
+      f32x2_unpack(f32x2_add(ls[0], ls[1]), la, lb);
+      f32x2_unpack(f32x2_add(ls[2], ls[3]), lc, ld);
+      l += (la + lb) + (lc + ld);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      mbar_arrive(&p_full[t][1]);
     }
 
     if (my_nkv > 0) {
