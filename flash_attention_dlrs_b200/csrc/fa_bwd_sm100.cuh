@@ -46,7 +46,7 @@ struct BwdCfg {
   static constexpr int kBoxBytes = 128 * 128;
   static constexpr int kBoxes = kD / 64;
   static constexpr int kStatBytes = 2 * 128 * 4;  // -lse and delta of one query block
-  static constexpr int kThreads = 320;
+  static constexpr int kThreads = 384;  // 8 elementwise warps + producer + MMA + 2 idle (complete the 3rd warpgroup)
   // stationary pair (2 tiles) + streamed pair ring (2 tiles per stage) + alignment slack
   static constexpr int kSmemDkdv = 2 * kTileBytes + kStages * 2 * kTileBytes + kStages * kStatBytes + 1024;
   static constexpr int kSmemDq = 2 * kTileBytes + kStages * 2 * kTileBytes + 1024;
@@ -75,9 +75,62 @@ __device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float 
   }
 }
 
+// Elementwise stage of one 64-column half (thread = one TMEM lane): P = exp2(S*sl2 - L), dS = P o (dP - delta),
+// both rounded to 16 bits and written back over S / dP as packed TMEM A operands.  Two fp32 lanes per issue slot
+// (FFMA2 / FADD2 / FMUL2).  kColStats: -L and -delta vary along the columns and come from shared memory (dK/dV
+// kernel, transposed scores); otherwise they are per-thread constants (dQ kernel).  kMask: causal diagonal block.
+// kStoreP: the dK/dV kernel needs P^T (for dV); the dQ kernel only needs dS, stored over S.
+template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP>
+__device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
+                                                     uint64_t nd_c, float sl2, int row, int col0) {
+  uint32_t sr[64], dr[64];
+  tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+  tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
+  tmem_ld_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+  tmem_ld_x32(tDP + 32, *reinterpret_cast<uint32_t(*)[32]>(&dr[32]));
+  tc_wait_ld();
+  const uint64_t sl2_2 = f32x2_pack(sl2, sl2);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t pp[16], pd[16];
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+      uint64_t nl4[2] = {nl_c, nl_c}, nd4[2] = {nd_c, nd_c};
+      if constexpr (kColStats) {
+        lds_f32x2x2(st_saddr + (c * 32 + g4 * 4) * 4, nl4[0], nl4[1]);
+        lds_f32x2x2(st_saddr + (128 + c * 32 + g4 * 4) * 4, nd4[0], nd4[1]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g4 * 2 + u;
+        const int e = c * 32 + g * 2;
+        float x0, x1;
+        f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl4[u]), x0, x1);
+        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        if constexpr (kMask) {
+          // keep key <= query.  Transposed scores: row = key, column = query; otherwise row = query, column = key.
+          const int c0 = col0 + e;
+          if (kTransposed ? (row > c0) : (c0 > row)) p0 = 0.f;
+          if (kTransposed ? (row > c0 + 1) : (c0 + 1 > row)) p1 = 0.f;
+        }
+        float d0, d1;
+        f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd4[u])), d0, d1);
+        if constexpr (kStoreP) pp[g] = pack2<kBf16>(p0, p1);
+        pd[g] = pack2<kBf16>(d0, d1);
+      }
+    }
+    if constexpr (kStoreP) {
+      tmem_st_x16(tS + c * 16, pp);
+      tmem_st_x16(tDP + c * 16, pd);
+    } else {
+      tmem_st_x16(tS + c * 16, pd);
+    }
+  }
+}
+
 // ================================================================================================ dK / dV
 template <bool kBf16, int kD, bool kCausal>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const BwdParams p) {
@@ -89,7 +142,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = sK + Cfg::kTileBytes;                   // stationary V_j
   uint8_t* sQ = sV + Cfg::kTileBytes;                   // [NS] streamed Q_i
   uint8_t* sDO = sQ + NS * Cfg::kTileBytes;             // [NS] streamed dO_i
-  float* sStat = reinterpret_cast<float*>(sDO + NS * Cfg::kTileBytes);  // [NS][2][128]: -lse, delta
+  float* sStat = reinterpret_cast<float*>(sDO + NS * Cfg::kTileBytes);  // [NS][2][128]: -lse, -delta
 
   __shared__ uint64_t kv_full, acc_full;
   __shared__ uint64_t in_full[NS], stat_full[NS], in_empty[NS];
@@ -130,6 +183,8 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  if (warp >= 8) {
+  setmaxnreg_dec<72>();
   if (warp == 8) {
     // ------------------------------------------------------------------ producer: TMA + row statistics
     if (lane == 0) {
@@ -159,7 +214,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int r = lane * 4 + e;
         const bool ok = q0 + r < p.N;
         st[r] = ok ? -lsep[q0 + r] : -INFINITY;  // rows past N: P = exp2(-inf) = 0
-        st[128 + r] = ok ? dlp[q0 + r] : 0.f;
+        st[128 + r] = ok ? -dlp[q0 + r] : 0.f;
       }
       mbar_arrive(&stat_full[s]);
     }
@@ -225,7 +280,9 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_commit(&acc_full);
     }
     __syncwarp();
+  }
   } else {
+    setmaxnreg_inc<216>();
     // ------------------------------------------------------------------ elementwise: P^T, dS^T  (warps 0-7)
     const int half = warp >> 2;
     const int row = (warp & 3) * 32 + lane;   // key row inside the block == TMEM lane
@@ -236,40 +293,14 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     for (int it = 0; it < n_it; ++it) {
       const int s = it % NS;
-      const bool diag = kCausal && (it == 0);          // query block == key block
       mbar_wait(&stat_full[s], (it / NS) & 1);
       mbar_wait(&sc_full[half], it & 1);
       tc_fence_after();
-      const float* st = sStat + s * 256 + half * 64;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sr[32], dr[32];
-        tmem_ld_x32(tS + c * 32, sr);
-        tmem_ld_x32(tDP + c * 32, dr);
-        tc_wait_ld();
-        uint32_t pp[16], pd[16];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 nl = *reinterpret_cast<const float4*>(st + c * 32 + g * 4);
-          const float4 dl = *reinterpret_cast<const float4*>(st + 128 + c * 32 + g * 4);
-          const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
-          float pv[4], dv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = half * 64 + c * 32 + g * 4 + e;   // query row inside the block
-            float x = ex2_approx(fmaf(__uint_as_float(sr[g * 4 + e]), sl2, nlv[e]));
-            if (diag && row > col) x = 0.f;                  // causal: keep key <= query
-            pv[e] = x;
-            dv[e] = x * (__uint_as_float(dr[g * 4 + e]) - dlv[e]);
-          }
-          pp[g * 2] = pack2<kBf16>(pv[0], pv[1]);
-          pp[g * 2 + 1] = pack2<kBf16>(pv[2], pv[3]);
-          pd[g * 2] = pack2<kBf16>(dv[0], dv[1]);
-          pd[g * 2 + 1] = pack2<kBf16>(dv[2], dv[3]);
-        }
-        tmem_st_x16(tS + c * 16, pp);
-        tmem_st_x16(tDP + c * 16, pd);
-      }
+      const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
+      if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
+        bwd_elementwise_half<kBf16, true, true, true, true>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64);
+      else
+        bwd_elementwise_half<kBf16, true, false, true, true>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[half]);
@@ -296,7 +327,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // ================================================================================================ dQ
 template <bool kBf16, int kD, bool kCausal>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                  const BwdParams p) {
@@ -347,6 +378,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  if (warp >= 8) {
+  setmaxnreg_dec<72>();
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
@@ -423,7 +456,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_commit(&acc_full);
     }
     __syncwarp();
+  }
   } else {
+    setmaxnreg_inc<216>();
     // ------------------------------------------------------------------ elementwise: dS  (warps 0-7)
     const int half = warp >> 2;
     const int row = (warp & 3) * 32 + lane;   // query row inside the block == TMEM lane
@@ -435,33 +470,16 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const bool in_range = q_row < p.N;
     const int64_t stat_idx = ((int64_t)b * p.H + h) * p.N + q_row;
     const float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
-    const float dl = in_range ? p.delta[stat_idx] : 0.f;
+    const float neg_dl = in_range ? -p.delta[stat_idx] : 0.f;
+    const uint64_t nl2 = f32x2_pack(neg_lse, neg_lse), nd2 = f32x2_pack(neg_dl, neg_dl);
 
     for (int it = 0; it < n_it; ++it) {
-      const bool diag = kCausal && (it == n_it - 1);   // key block == query block
       mbar_wait(&sc_full[half], it & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sr[32], dr[32];
-        tmem_ld_x32(tS + c * 32, sr);
-        tmem_ld_x32(tDP + c * 32, dr);
-        tc_wait_ld();
-        uint32_t pd[16];
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          float dv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = half * 64 + c * 32 + g * 2 + e;   // key row inside the block
-            float x = ex2_approx(fmaf(__uint_as_float(sr[g * 2 + e]), sl2, neg_lse));
-            if (diag && col > row) x = 0.f;                  // causal: keep key <= query
-            dv[e] = x * (__uint_as_float(dr[g * 2 + e]) - dl);
-          }
-          pd[g] = pack2<kBf16>(dv[0], dv[1]);
-        }
-        tmem_st_x16(tS + c * 16, pd);
-      }
+      if (kCausal && it == n_it - 1)   // key block == query block
+        bwd_elementwise_half<kBf16, false, true, false, false>(tS, tDP, 0u, nl2, nd2, sl2, row, half * 64);
+      else
+        bwd_elementwise_half<kBf16, false, false, false, false>(tS, tDP, 0u, nl2, nd2, sl2, row, half * 64);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[half]);

@@ -324,6 +324,11 @@ __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// 16-byte shared-memory load as two packed fp32 pairs (explicit .shared so the compiler does not fall back to
+// generic loads when the pointer's address space is not provable)
+__device__ __forceinline__ void lds_f32x2x2(uint32_t saddr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
+}
 // per-warpgroup register re-budgeting (all four warps of the warpgroup execute it)
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_inc() {
