@@ -15,7 +15,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "libfa_b200.so"
+# FA_B200_LIB points at an alternative build of the same ABI (profiling / ablation builds); default is in-tree.
+LIB_PATH = Path(os.environ["FA_B200_LIB"]) if os.environ.get("FA_B200_LIB") else PKG_DIR / "libfa_b200.so"
 HEADER = REPO_ROOT / "include" / "fa_b200.h"
 
 FA_DTYPE_F16, FA_DTYPE_BF16, FA_DTYPE_F32 = 0, 1, 2

@@ -52,6 +52,8 @@ struct BwdCfg {
   static constexpr int kSmemDq = 2 * kTileBytes + kStages * 2 * kTileBytes + 1024;
   // TMEM columns
   static constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemAcc0 = 256, kTmemAcc1 = 256 + kD;
+  // dQ kernel only: Q_i and dO_i as TMEM-resident A operands (packed 16-bit pairs, D/2 columns each)
+  static constexpr uint32_t kTmemQA = 256 + kD, kTmemDOA = 256 + kD + kD / 2;
 };
 
 // TMEM accumulator rows -> 16-bit global rows: thread = one row, `ncols` fp32 columns starting at taddr.
@@ -83,6 +85,9 @@ __device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float 
 template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP>
 __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
                                                      uint64_t nd_c, float sl2, int row, int col0) {
+#if FA_ABLATE == 3
+  return;
+#endif
   uint32_t sr[64], dr[64];
   tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
   tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
@@ -104,6 +109,11 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
       for (int u = 0; u < 2; ++u) {
         const int g = g4 * 2 + u;
         const int e = c * 32 + g * 2;
+#if FA_ABLATE == 2
+        if constexpr (kStoreP) pp[g] = sr[e] ^ sr[e + 1];
+        pd[g] = dr[e] ^ dr[e + 1];
+        continue;
+#endif
         float x0, x1;
         f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl4[u]), x0, x1);
         float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
@@ -223,36 +233,37 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (elect_one()) {
       constexpr uint32_t idesc_sc = umma_idesc_f16(kBf16, 128, 64, 0, 0);   // [128 kv] x [64 q], K = D
       constexpr uint32_t idesc_gr = umma_idesc_f16(kBf16, 128, kD, 0, 1);   // [128 kv] x [D],   K = 64 q
-      const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO);
+      constexpr uint32_t kTileLo = Cfg::kTileBytes >> 4, kHalfLo = 8192u >> 4;
+      const uint32_t k_lo = umma_lo_kmajor(smem_u32(sK)), v_lo = umma_lo_kmajor(smem_u32(sV));
+      const uint32_t q_lo = umma_lo_kmajor(smem_u32(sQ)), do_lo = umma_lo_kmajor(smem_u32(sDO));
+      const uint32_t q_mn = umma_lo_mnmajor(smem_u32(sQ), Cfg::kBoxBytes);
+      const uint32_t do_mn = umma_lo_mnmajor(smem_u32(sDO), Cfg::kBoxBytes);
 
       // S^T half = K_j Q_i[half]^T ; dP^T half = V_j dO_i[half]^T
       auto issue_score = [&](int half, int s) {
+        const uint32_t bq = q_lo + s * kTileLo + half * kHalfLo, bdo = do_lo + s * kTileLo + half * kHalfLo;
+        const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          uint64_t da = umma_desc_kmajor(sK_a + (k / 4) * Cfg::kBoxBytes, k % 4);
-          uint64_t db = umma_desc_kmajor(sQ_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
-          umma_ss(tmem + Cfg::kTmemS + half * 64, da, db, idesc_sc, k > 0);
-        }
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss_lo(dS, k_lo + umma_koff_kmajor(k, Cfg::kBoxBytes), bq + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_sc,
+                     k > 0);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          uint64_t da = umma_desc_kmajor(sV_a + (k / 4) * Cfg::kBoxBytes, k % 4);
-          uint64_t db = umma_desc_kmajor(sDO_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
-          umma_ss(tmem + Cfg::kTmemDP + half * 64, da, db, idesc_sc, k > 0);
-        }
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss_lo(dDP, v_lo + umma_koff_kmajor(k, Cfg::kBoxBytes), bdo + umma_koff_kmajor(k, Cfg::kBoxBytes),
+                     idesc_sc, k > 0);
         tc_commit(&sc_full[half]);
       };
       // dV += P^T[half] dO_i[half] ; dK += dS^T[half] Q_i[half]
       auto issue_grad = [&](int half, int s, bool first) {
+        const uint32_t bdo = do_mn + s * kTileLo + half * umma_koff_mnmajor(4);
+        const uint32_t bq = q_mn + s * kTileLo + half * umma_koff_mnmajor(4);
+        const uint32_t aP = tmem + Cfg::kTmemS + half * 64, aDS = tmem + Cfg::kTmemDP + half * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t db = umma_desc_mnmajor(sDO_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, half * 4 + k);
-          umma_ts(tmem + Cfg::kTmemAcc0, tmem + Cfg::kTmemS + half * 64 + k * 8, db, idesc_gr, !(first && k == 0));
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_ts_lo(tmem + Cfg::kTmemAcc0, aP + k * 8, bdo + umma_koff_mnmajor(k), idesc_gr, !(first && k == 0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t db = umma_desc_mnmajor(sQ_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, half * 4 + k);
-          umma_ts(tmem + Cfg::kTmemAcc1, tmem + Cfg::kTmemDP + half * 64 + k * 8, db, idesc_gr, !(first && k == 0));
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_ts_lo(tmem + Cfg::kTmemAcc1, aDS + k * 8, bq + umma_koff_mnmajor(k), idesc_gr, !(first && k == 0));
       };
 
       mbar_wait(&kv_full, 0);
@@ -340,7 +351,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sK = sDO + Cfg::kTileBytes;                  // [NS] streamed K_j
   uint8_t* sV = sK + NS * Cfg::kTileBytes;              // [NS] streamed V_j
 
-  __shared__ uint64_t qdo_full, acc_full;
+  __shared__ uint64_t qdo_full, qdo_tmem, acc_full;
   __shared__ uint64_t in_full[NS], in_empty[NS];
   __shared__ uint64_t sc_full[2], p_full[2];
   __shared__ uint32_t tmem_base_s;
@@ -355,6 +366,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(&qdo_full, 1);
+    mbar_init(&qdo_tmem, 256);
     mbar_init(&acc_full, 1);
     for (int s = 0; s < NS; ++s) {
       mbar_init(&in_full[s], 1);
@@ -404,34 +416,32 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (elect_one()) {
       constexpr uint32_t idesc_sc = umma_idesc_f16(kBf16, 128, 64, 0, 0);   // [128 q] x [64 kv], K = D
       constexpr uint32_t idesc_gr = umma_idesc_f16(kBf16, 128, kD, 0, 1);   // [128 q] x [D],    K = 64 kv
-      const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO);
+      constexpr uint32_t kTileLo = Cfg::kTileBytes >> 4, kHalfLo = 8192u >> 4;
+      const uint32_t k_lo = umma_lo_kmajor(smem_u32(sK)), v_lo = umma_lo_kmajor(smem_u32(sV));
+      const uint32_t k_mn = umma_lo_mnmajor(smem_u32(sK), Cfg::kBoxBytes);
 
-      // S half = Q_i K_j[half]^T ; dP half = dO_i V_j[half]^T
+      // S half = Q_i K_j[half]^T ; dP half = dO_i V_j[half]^T      (A operands resident in TMEM)
       auto issue_score = [&](int half, int s) {
+        const uint32_t bk = k_lo + s * kTileLo + half * kHalfLo, bv = v_lo + s * kTileLo + half * kHalfLo;
+        const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          uint64_t da = umma_desc_kmajor(sQ_a + (k / 4) * Cfg::kBoxBytes, k % 4);
-          uint64_t db = umma_desc_kmajor(sK_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
-          umma_ss(tmem + Cfg::kTmemS + half * 64, da, db, idesc_sc, k > 0);
-        }
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ts_lo(dS, tmem + Cfg::kTmemQA + k * 8, bk + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_sc, k > 0);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          uint64_t da = umma_desc_kmajor(sDO_a + (k / 4) * Cfg::kBoxBytes, k % 4);
-          uint64_t db = umma_desc_kmajor(sV_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes + half * 8192, k % 4);
-          umma_ss(tmem + Cfg::kTmemDP + half * 64, da, db, idesc_sc, k > 0);
-        }
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ts_lo(dDP, tmem + Cfg::kTmemDOA + k * 8, bv + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_sc, k > 0);
         tc_commit(&sc_full[half]);
       };
       // dQ += dS[half] K_j[half]
       auto issue_grad = [&](int half, int s, bool first) {
+        const uint32_t bk = k_mn + s * kTileLo + half * umma_koff_mnmajor(4);
+        const uint32_t aDS = tmem + Cfg::kTmemS + half * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t db = umma_desc_mnmajor(sK_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, half * 4 + k);
-          umma_ts(tmem + Cfg::kTmemAcc0, tmem + Cfg::kTmemS + half * 64 + k * 8, db, idesc_gr, !(first && k == 0));
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_ts_lo(tmem + Cfg::kTmemAcc0, aDS + k * 8, bk + umma_koff_mnmajor(k), idesc_gr, !(first && k == 0));
       };
 
-      mbar_wait(&qdo_full, 0);
+      mbar_wait(&qdo_tmem, 0);
       mbar_wait(&in_full[0], 0);
       tc_fence_after();
       issue_score(0, 0);
@@ -472,6 +482,30 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
     const float neg_dl = in_range ? -p.delta[stat_idx] : 0.f;
     const uint64_t nl2 = f32x2_pack(neg_lse, neg_lse), nd2 = f32x2_pack(neg_dl, neg_dl);
+
+    // Stationary operands: warpgroup a moves Q_i, warpgroup b moves dO_i from the (swizzled) TMA tile into TMEM,
+    // row r -> lane r, elements (2c, 2c+1) -> column c.  As TMEM A operands they cost no shared-memory bandwidth
+    // in the score MMAs (an SS MMA with N = 64 needs 192 B/clk of smem reads, above the 128 B/clk an SM has).
+    {
+      mbar_wait(&qdo_full, 0);
+      const uint32_t src = smem_u32(half == 0 ? sQ : sDO);
+      const uint32_t dstA = tmem + (half == 0 ? Cfg::kTmemQA : Cfg::kTmemDOA) + lane_base;
+#pragma unroll
+      for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
+        uint32_t v[32];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t a = src + bx * Cfg::kBoxBytes + sw128_offset(row, ch);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[ch * 4]), "=r"(v[ch * 4 + 1]), "=r"(v[ch * 4 + 2]), "=r"(v[ch * 4 + 3])
+                       : "r"(a));
+        }
+        tmem_st_x32(dstA + bx * 32, v);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&qdo_tmem);
+    }
 
     for (int it = 0; it < n_it; ++it) {
       mbar_wait(&sc_full[half], it & 1);

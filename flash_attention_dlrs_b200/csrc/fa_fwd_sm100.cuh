@@ -136,7 +136,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(kBf16, 128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(kBf16, 128, kD, 0, 1);
-      const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+      const uint32_t qlo = umma_lo_kmajor(smem_u32(sQ)), klo = umma_lo_kmajor(smem_u32(sK));
+      const uint32_t vlo = umma_lo_mnmajor(smem_u32(sV), Cfg::kBoxBytes);
+      constexpr uint32_t kTileLo = Cfg::kTileBytes >> 4;
       auto tS = [&](int t) { return tmem + (t ? Cfg::kTmemS1 : Cfg::kTmemS0); };
       auto tO = [&](int t) { return tmem + (t ? Cfg::kTmemO1 : Cfg::kTmemO0); };
 
@@ -144,12 +146,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int s = j % NS;
         mbar_wait(&k_full[s], (j / NS) & 1);
         tc_fence_after();
+        const uint32_t a0 = qlo + t * kTileLo, b0 = klo + s * kTileLo;
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          uint64_t da = umma_desc_kmajor(sQ_a + t * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes, k % 4);
-          uint64_t db = umma_desc_kmajor(sK_a + s * Cfg::kTileBytes + (k / 4) * Cfg::kBoxBytes, k % 4);
-          umma_ss(tS(t), da, db, idesc_s, k > 0);
-        }
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss_lo(tS(t), a0 + umma_koff_kmajor(k, Cfg::kBoxBytes), b0 + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_s,
+                     k > 0);
         tc_commit(&s_full[t]);
         // last tile that reads K block j releases the stage
         const bool last_user = (t == 1) || (nkv[1] <= j);
@@ -171,10 +172,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_wait(&p_full[t][hf], j & 1);
             tc_fence_after();
 #pragma unroll
-            for (int k = hf * 4; k < hf * 4 + 4; ++k) {
-              uint64_t db = umma_desc_mnmajor(sV_a + s * Cfg::kTileBytes, Cfg::kBoxBytes, k);
-              umma_ts(tO(t), tS(t) + k * 8, db, idesc_o, (j > 0) || (k > 0));
-            }
+            for (int k = hf * 4; k < hf * 4 + 4; ++k)
+              umma_ts_lo(tO(t), tS(t) + k * 8, vlo + s * kTileLo + umma_koff_mnmajor(k), idesc_o, (j > 0) || (k > 0));
           }
           tc_commit(&o_full[t]);
           const bool last_user = (t == 1) || (nkv[1] <= j);
@@ -201,6 +200,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int j = 0; j < my_nkv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+#if FA_ABLATE == 3
+      tc_fence_before();
+      mbar_arrive(&p_full[t][0]);
+      mbar_arrive(&p_full[t][1]);
+      l = 1.f;
+      m_used = 0.f;
+      continue;
+#endif
       uint32_t sr[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
@@ -255,6 +262,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
+#if FA_ABLATE == 2
+          pk[i] = sr[c * 32 + 2 * i] ^ sr[c * 32 + 2 * i + 1];
+          continue;
+#endif
           const uint64_t x2 = f32x2_fma(f32x2_pack_bits(sr[c * 32 + 2 * i], sr[c * 32 + 2 * i + 1]), sl2_2, nm2);
           float x0, x1;
           f32x2_unpack(x2, x0, x1);

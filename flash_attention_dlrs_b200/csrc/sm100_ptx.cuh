@@ -194,6 +194,52 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t box0_addr, uint32
   return umma_smem_desc_sw128(box0_addr + k16 * 2048u, box_stride_bytes, 1024u);
 }
 
+// Cheap per-MMA descriptor arithmetic for the issue loops.  With SWIZZLE_128B, SBO = 1024 B and version 1 the high
+// word of every descriptor used here is the same constant; the low word is (address >> 4) | (LBO >> 4) << 16, and
+// stepping through K (or selecting a ring stage / a 64-row half) only adds a constant to the low word (shared
+// memory addresses stay below 2^18, so the 14-bit address field never carries).
+constexpr uint32_t kUmmaDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_lo_kmajor(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t umma_lo_mnmajor(uint32_t saddr, uint32_t box_stride_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | ((box_stride_bytes >> 4) << 16);
+}
+// low-word offset of K step k (16 elements) inside a K-major tile made of 64-column boxes of `box_bytes`
+__host__ __device__ constexpr uint32_t umma_koff_kmajor(int k, int box_bytes) {
+  return (uint32_t)(((k / 4) * box_bytes + (k % 4) * 32) >> 4);
+}
+// low-word offset of K step k16 (16 rows of 128 B) inside an MN-major tile
+__host__ __device__ constexpr uint32_t umma_koff_mnmajor(int k16) { return (uint32_t)((k16 * 2048) >> 4); }
+
+__device__ __forceinline__ void umma_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 (fp16/bf16 inputs, fp32 accumulate).
 //   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major  [16] B major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
@@ -285,10 +331,19 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 // ----------------------------------------------------------------------------------------------
 // small math / packing helpers
 // ----------------------------------------------------------------------------------------------
+// FA_ABLATE (timing experiments only, results are wrong): 1 = no MUFU (exp2 -> identity),
+// 2 = elementwise stages only move data TMEM -> registers -> TMEM, 3 = elementwise stages skipped.
+#ifndef FA_ABLATE
+#define FA_ABLATE 0
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
+#if FA_ABLATE == 1
+  return x;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
