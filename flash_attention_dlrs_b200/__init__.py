@@ -4,9 +4,11 @@ include/fa_b200.h (libfa_b200.so).  No Triton, no autotune, no CPU fallback."""
 from .flash_attention_torch import (  # noqa: F401
     FlashAttention, FlashAttentionDeterministic, convert_triton_dtype, flash_attention)
 from .flash_attention_wrappers import flash_attention_backward, flash_attention_forward  # noqa: F401
+from .host_pipeline import HostAttentionPipeline, attention_from_host  # noqa: F401
 from .sharding import head_range, head_sharded_attention  # noqa: F401
 
 __all__ = [
     "FlashAttention", "FlashAttentionDeterministic", "convert_triton_dtype", "flash_attention",
     "flash_attention_forward", "flash_attention_backward", "head_range", "head_sharded_attention",
+    "HostAttentionPipeline", "attention_from_host",
 ]
