@@ -268,13 +268,26 @@ def run_ours(args):
     from flash_attention_dlrs_b200 import HostAttentionPipeline
 
     out_host = [torch.empty(B, H, N, D, dtype=dtype).pin_memory() for _ in range(4)]  # O, dQ, dK, dV
-    pipe = HostAttentionPipeline(B, H, N, D, dtype, dev, chunks=8, with_backward=True)
+    # full-duplex copies are faster on most hosts; some collapse under simultaneous traffic: calibrate, keep the faster
+    best = None
+    for duplex in (True, False):
+        cand = HostAttentionPipeline(B, H, N, D, dtype, dev, chunks=16, with_backward=True, duplex=duplex)
+        cand.run(host, out_host, causal, scale).synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            cand.run(host, out_host, causal, scale)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, cand, duplex)
+        else:
+            del cand
+    pipe, duplex_used = best[1], best[2]
 
     def e2e_step():
         return pipe.run(host, out_host, causal, scale)
 
-    for _ in range(2):
-        e2e_step().synchronize()
+    e2e_step().synchronize()
     # the pipelined path must reproduce the resident-input path bit for bit
     O_chk, L_chk = _native.forward(Q, K, V, causal, scale)
     g_chk = _native.backward(Q, K, V, O_chk, dO, L_chk, causal, scale)
@@ -296,8 +309,8 @@ def run_ours(args):
     io_bytes = 4 * B * H * N * D * 2
     e2e = {"value": job_flops / (e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e_ms,
            "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
-           "api": "HostAttentionPipeline.run((Q,K,V,dO) pinned host -> (O,dQ,dK,dV) pinned host), 8 head chunks, "
-                  "copies overlapped with the kernels",
+           "api": "HostAttentionPipeline.run((Q,K,V,dO) pinned host -> (O,dQ,dK,dV) pinned host), 16 head chunks, "
+                  "copies overlapped with the kernels, duplex=%s" % duplex_used,
            "pcie_gbs_each_way": io_bytes / (e_ms * 1e-3) / 1e9}
 
     if rank == 0:

@@ -23,7 +23,10 @@ class HostAttentionPipeline:
     """Reusable pipeline for one problem shape: owns the device staging buffers, streams and events."""
 
     def __init__(self, B: int, H: int, N: int, D: int, dtype: torch.dtype, device, chunks: int = 8,
-                 with_backward: bool = True):
+                 with_backward: bool = True, duplex: bool = True):
+        """duplex=True puts host->device and device->host copies on separate streams (full-duplex PCIe); on hosts
+        where simultaneous traffic in both directions collapses the link rate, duplex=False keeps one copy stream and
+        only overlaps the copies with the kernels."""
         self.shape = (B, H, N, D)
         self.dtype, self.device = dtype, torch.device(device)
         BH = B * H
@@ -39,7 +42,7 @@ class HostAttentionPipeline:
         self.inp = [[mk() for _ in range(n_in)] for _ in range(2)]
         self.out = [[mk() for _ in range(n_out)] for _ in range(2)]
         self.s_in = torch.cuda.Stream(self.device)
-        self.s_out = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device) if duplex else self.s_in
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_done = [torch.cuda.Event() for _ in range(2)]
         self.ev_in_free = [torch.cuda.Event() for _ in range(2)]
@@ -94,7 +97,7 @@ class HostAttentionPipeline:
 
 
 def attention_from_host(Q, K, V, dO=None, causal: bool = False, softmax_scale: float = 1.0, device="cuda",
-                        chunks: int = 8, out=None):
+                        chunks: int = 8, out=None, duplex: bool = True):
     """One-shot convenience wrapper: pinned host tensors in, pinned host tensors out (O, or O, dQ, dK, dV with dO)."""
     if Q.dim() != 4 or Q.shape != K.shape or Q.shape != V.shape:
         raise ValueError("Q, K, V must all be of shape (B, H, N, d)")
@@ -102,7 +105,7 @@ def attention_from_host(Q, K, V, dO=None, causal: bool = False, softmax_scale: f
         raise ValueError("attention_from_host expects pinned host tensors")
     _native.dtype_code(Q.dtype)
     B, H, N, D = Q.shape
-    pipe = HostAttentionPipeline(B, H, N, D, Q.dtype, device, chunks, with_backward=dO is not None)
+    pipe = HostAttentionPipeline(B, H, N, D, Q.dtype, device, chunks, with_backward=dO is not None, duplex=duplex)
     n_out = 4 if dO is not None else 1
     if out is None:
         out = [torch.empty(Q.shape, dtype=Q.dtype).pin_memory() for _ in range(n_out)]

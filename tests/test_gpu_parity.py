@@ -335,6 +335,7 @@ def test_config4_long_context_full_size():
 
     # (1) row-subset oracle in float64 on the CPU: rows of P need only q_i and all keys <= i
     rows = [0, 1, 127, 128, 4097, 16383, 20000, 32767]
+    dq_head_max = dQ[0].float().abs().amax(dim=(1, 2)).double().cpu()
     for h in (0, 37, 63):
         k64, v64 = K[0, h].double().cpu(), V[0, h].double().cpu()
         for i in rows:
@@ -351,7 +352,8 @@ def test_config4_long_context_full_size():
             dp = v64[: i + 1] @ do
             ds = p * (dp - (o_ref * do).sum())
             dq_ref = scale * (ds @ k64[: i + 1])
-            e = (dQ[0, h, i].double().cpu() - dq_ref).abs().max() / dq_ref.abs().max().clamp_min(1e-3)
+            # same normalisation as everywhere else: the tensor-level max |dQ| (of this head), not the row's own
+            e = (dQ[0, h, i].double().cpu() - dq_ref).abs().max() / dq_head_max[h]
             assert e.item() <= 1e-2, f"dQ row {i} head {h}: {e.item():.3e}"
 
     # (2) checksums: rows of P sum to one  =>  sum_j dV_j = sum_i dO_i ;  rows of dS sum to zero  =>  sum_j dK_j = 0
