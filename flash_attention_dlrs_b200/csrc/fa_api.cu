@@ -135,6 +135,16 @@ int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaSt
 
 }  // namespace
 
+#if FA_TRACE
+// debug builds only (not declared in include/fa_b200.h)
+extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
+  long long* p = static_cast<long long*>(dev_buf);
+  cudaMemcpyToSymbol(fa::g_fa_trace, &p, sizeof(p));
+  cudaMemcpyToSymbol(fa::g_fa_trace_cap, &capacity_events, sizeof(int));
+  return 0;
+}
+#endif
+
 extern "C" {
 
 int fa_version(void) { return 1; }

@@ -49,7 +49,10 @@ struct BwdCfg {
   static constexpr int kThreads = 384;  // 8 elementwise warps + producer + MMA + 2 idle (complete the 3rd warpgroup)
   // stationary pair (2 tiles) + streamed pair ring (2 tiles per stage) + alignment slack
   static constexpr int kSmemDkdv = 2 * kTileBytes + kStages * 2 * kTileBytes + kStages * kStatBytes + 1024;
-  static constexpr int kSmemDq = 2 * kTileBytes + kStages * 2 * kTileBytes + 1024;
+  // dQ kernel: Q_i/dO_i staging (2 tiles) + 3-stage K ring (K_j is held from its score MMAs until its dQ MMAs, one
+  // block later) + 2-stage V ring
+  static constexpr int kStagesK = 3, kStagesV = 2;
+  static constexpr int kSmemDq = 2 * kTileBytes + (kStagesK + kStagesV) * kTileBytes + 1024;
   // TMEM columns
   static constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemAcc0 = 256, kTmemAcc1 = 256 + kD;
   // dQ kernel only: Q_i and dO_i as TMEM-resident A operands (packed 16-bit pairs, D/2 columns each)
@@ -135,6 +138,47 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
     } else {
       tmem_st_x16(tS + c * 16, pd);
     }
+  }
+}
+
+// dQ kernel flavour: per-thread statistics, dS only.  The two score accumulators are copied to registers first and
+// released to the MMA warp (`sc_free`) before any arithmetic, so the next block's score MMAs overlap this stage.
+// Output: 64 values of this thread's row as 32 packed 16-bit pairs in `pd`.
+template <bool kBf16, bool kMask>
+__device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
+                                                    uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32]) {
+  uint32_t sr[64], dr[64];
+  tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+  tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
+  tmem_ld_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+  tmem_ld_x32(tDP + 32, *reinterpret_cast<uint32_t(*)[32]>(&dr[32]));
+  tc_wait_ld();
+  tc_fence_before();
+  mbar_arrive(sc_free_bar);
+#if FA_ABLATE == 3
+#pragma unroll
+  for (int g = 0; g < 32; ++g) pd[g] = 0;
+  return;
+#endif
+  const uint64_t sl2_2 = f32x2_pack(sl2, sl2);
+#pragma unroll
+  for (int g = 0; g < 32; ++g) {
+    const int e = g * 2;
+#if FA_ABLATE == 2
+    pd[g] = sr[e] ^ dr[e + 1];
+    continue;
+#endif
+    float x0, x1;
+    f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl), x0, x1);
+    float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+    if constexpr (kMask) {   // causal diagonal block: keep key <= query (row = query, column = key)
+      const int c0 = col0 + e;
+      if (c0 > row) p0 = 0.f;
+      if (c0 + 1 > row) p1 = 0.f;
+    }
+    float d0, d1;
+    f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd)), d0, d1);
+    pd[g] = pack2<kBf16>(d0, d1);
   }
 }
 
@@ -243,14 +287,16 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       auto issue_score = [&](int half, int s) {
         const uint32_t bq = q_lo + s * kTileLo + half * kHalfLo, bdo = do_lo + s * kTileLo + half * kHalfLo;
         const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss_lo(dS, k_lo + umma_koff_kmajor(k, Cfg::kBoxBytes), bq + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_sc,
-                     k > 0);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss_lo(dDP, v_lo + umma_koff_kmajor(k, Cfg::kBoxBytes), bdo + umma_koff_kmajor(k, Cfg::kBoxBytes),
-                     idesc_sc, k > 0);
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+          umma_ss_off<off, off>(dS, k_lo, bq, idesc_sc, k > 0);
+        });
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+          umma_ss_off<off, off>(dDP, v_lo, bdo, idesc_sc, k > 0);
+        });
         tc_commit(&sc_full[half]);
       };
       // dV += P^T[half] dO_i[half] ; dK += dS^T[half] Q_i[half]
@@ -258,12 +304,15 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t bdo = do_mn + s * kTileLo + half * umma_koff_mnmajor(4);
         const uint32_t bq = q_mn + s * kTileLo + half * umma_koff_mnmajor(4);
         const uint32_t aP = tmem + Cfg::kTmemS + half * 64, aDS = tmem + Cfg::kTmemDP + half * 64;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts_lo(tmem + Cfg::kTmemAcc0, aP + k * 8, bdo + umma_koff_mnmajor(k), idesc_gr, !(first && k == 0));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts_lo(tmem + Cfg::kTmemAcc1, aDS + k * 8, bq + umma_koff_mnmajor(k), idesc_gr, !(first && k == 0));
+        const uint32_t dV_t = tmem + Cfg::kTmemAcc0, dK_t = tmem + Cfg::kTmemAcc1;
+        static_for<0, 4>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dV_t, aP, bdo, idesc_gr, !(first && k == 0));
+        });
+        static_for<0, 4>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dK_t, aDS, bq, idesc_gr, !(first && k == 0));
+        });
       };
 
       mbar_wait(&kv_full, 0);
@@ -343,17 +392,17 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                  const BwdParams p) {
   using Cfg = BwdCfg<kD>;
-  constexpr int NS = Cfg::kStages;
+  constexpr int NK = Cfg::kStagesK, NV = Cfg::kStagesV;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // stationary Q_i
   uint8_t* sDO = sQ + Cfg::kTileBytes;                  // stationary dO_i
-  uint8_t* sK = sDO + Cfg::kTileBytes;                  // [NS] streamed K_j
-  uint8_t* sV = sK + NS * Cfg::kTileBytes;              // [NS] streamed V_j
+  uint8_t* sK = sDO + Cfg::kTileBytes;                  // [NK] streamed K_j
+  uint8_t* sV = sK + NK * Cfg::kTileBytes;              // [NV] streamed V_j
 
   __shared__ uint64_t qdo_full, qdo_tmem, acc_full;
-  __shared__ uint64_t in_full[NS], in_empty[NS];
-  __shared__ uint64_t sc_full[2], p_full[2];
+  __shared__ uint64_t k_full[NK], k_empty[NK], v_full[NV], v_empty[NV];
+  __shared__ uint64_t sc_full[2], sc_free[2], p_full[2], ds_free[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -368,13 +417,19 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(&qdo_full, 1);
     mbar_init(&qdo_tmem, 256);
     mbar_init(&acc_full, 1);
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&in_full[s], 1);
-      mbar_init(&in_empty[s], 1);
+    for (int s = 0; s < NK; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < NV; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&sc_full[t], 1);
+      mbar_init(&sc_free[t], 128);
       mbar_init(&p_full[t], 128);
+      mbar_init(&ds_free[t], 1);
     }
     fence_mbar_init();
   }
@@ -401,13 +456,15 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_4d(sDO + bx * Cfg::kBoxBytes, &tmDO, &qdo_full, bx * 64, q0, h, b);
       }
       for (int it = 0; it < n_it; ++it) {
-        const int s = it % NS;
-        mbar_wait(&in_empty[s], ((it / NS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&in_full[s], 2 * Cfg::kTileBytes);
-        for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
-          tma_load_4d(sK + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &in_full[s], bx * 64, it * 128, h, b);
-          tma_load_4d(sV + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &in_full[s], bx * 64, it * 128, h, b);
-        }
+        const int sk = it % NK, sv = it % NV;
+        mbar_wait(&k_empty[sk], ((it / NK) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[sk], Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(sK + sk * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &k_full[sk], bx * 64, it * 128, h, b);
+        mbar_wait(&v_empty[sv], ((it / NV) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], Cfg::kTileBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(sV + sv * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &v_full[sv], bx * 64, it * 128, h, b);
       }
     }
     __syncwarp();
@@ -421,47 +478,72 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t k_mn = umma_lo_mnmajor(smem_u32(sK), Cfg::kBoxBytes);
 
       // S half = Q_i K_j[half]^T ; dP half = dO_i V_j[half]^T      (A operands resident in TMEM)
-      auto issue_score = [&](int half, int s) {
-        const uint32_t bk = k_lo + s * kTileLo + half * kHalfLo, bv = v_lo + s * kTileLo + half * kHalfLo;
+      auto issue_score = [&](int half, int sk, int sv) {
+        const uint32_t bk = k_lo + sk * kTileLo + half * kHalfLo, bv = v_lo + sv * kTileLo + half * kHalfLo;
         const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ts_lo(dS, tmem + Cfg::kTmemQA + k * 8, bk + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_sc, k > 0);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ts_lo(dDP, tmem + Cfg::kTmemDOA + k * 8, bv + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_sc, k > 0);
+        const uint32_t aQ = tmem + Cfg::kTmemQA, aDO = tmem + Cfg::kTmemDOA;
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ts_off<k * 8, umma_koff_kmajor(k, Cfg::kBoxBytes)>(dS, aQ, bk, idesc_sc, k > 0);
+        });
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ts_off<k * 8, umma_koff_kmajor(k, Cfg::kBoxBytes)>(dDP, aDO, bv, idesc_sc, k > 0);
+        });
         tc_commit(&sc_full[half]);
       };
       // dQ += dS[half] K_j[half]
+      // dS half lives in shared memory (one 128 x 64 swizzled box per half, K-major A operand): sdS[a] reuses the
+      // first box of the Q_i staging tile, sdS[b] the first box of the dO_i staging tile (both dead after the TMEM copy).
+      const uint32_t ds_lo[2] = {umma_lo_kmajor(smem_u32(sQ)), umma_lo_kmajor(smem_u32(sDO))};
+      constexpr uint32_t idesc_gs = umma_idesc_f16(kBf16, 128, kD, 0, 1);
       auto issue_grad = [&](int half, int s, bool first) {
         const uint32_t bk = k_mn + s * kTileLo + half * umma_koff_mnmajor(4);
-        const uint32_t aDS = tmem + Cfg::kTmemS + half * 64;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts_lo(tmem + Cfg::kTmemAcc0, aDS + k * 8, bk + umma_koff_mnmajor(k), idesc_gr, !(first && k == 0));
+        const uint32_t dQ_t = tmem + Cfg::kTmemAcc0, aDS = ds_lo[half];
+        static_for<0, 4>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ss_off<umma_koff_kmajor(k, Cfg::kBoxBytes), umma_koff_mnmajor(k)>(dQ_t, aDS, bk, idesc_gs,
+                                                                                !(first && k == 0));
+        });
+        tc_commit(&ds_free[half]);
       };
 
       mbar_wait(&qdo_tmem, 0);
-      mbar_wait(&in_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      mbar_wait(&v_full[0], 0);
       tc_fence_after();
-      issue_score(0, 0);
-      issue_score(1, 0);
+      issue_score(0, 0, 0);
+      issue_score(1, 0, 0);
+      tc_commit(&v_empty[0]);
       for (int it = 0; it < n_it; ++it) {
-        const int s = it % NS, sn = (it + 1) % NS;
+        const int sk = it % NK, skn = (it + 1) % NK, svn = (it + 1) % NV;
         const bool more = it + 1 < n_it;
-        mbar_wait(&p_full[0], it & 1);
-        tc_fence_after();
-        issue_grad(0, s, it == 0);
+        // the score accumulators are free as soon as the elementwise warps hold them in registers: the next
+        // scores run on the tensor core while dS is being computed
+        fa_trace(0, it, 0);
         if (more) {
-          mbar_wait(&in_full[sn], ((it + 1) / NS) & 1);
+          mbar_wait(&sc_free[0], it & 1);
+          mbar_wait(&k_full[skn], ((it + 1) / NK) & 1);
+          mbar_wait(&v_full[svn], ((it + 1) / NV) & 1);
           tc_fence_after();
-          issue_score(0, sn);
+          issue_score(0, skn, svn);
+          fa_trace(0, it, 1);
+          mbar_wait(&sc_free[1], it & 1);
+          tc_fence_after();
+          issue_score(1, skn, svn);
+          tc_commit(&v_empty[svn]);
         }
-        mbar_wait(&p_full[1], it & 1);
+        fa_trace(0, it, 2);
+        mbar_wait(&p_full[0], it & 1);
+        fa_trace(0, it, 3);
         tc_fence_after();
-        issue_grad(1, s, false);
-        tc_commit(&in_empty[s]);
-        if (more) issue_score(1, sn);
+        issue_grad(0, sk, it == 0);
+        mbar_wait(&p_full[1], it & 1);
+        fa_trace(0, it, 4);
+        tc_fence_after();
+        issue_grad(1, sk, false);
+        tc_commit(&k_empty[sk]);
+        fa_trace(0, it, 5);
       }
       tc_commit(&acc_full);
     }
@@ -507,16 +589,26 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_arrive(&qdo_tmem);
     }
 
+    const uint32_t sds = smem_u32(half == 0 ? sQ : sDO);   // this half's dS box (see the MMA warp)
     for (int it = 0; it < n_it; ++it) {
+      if (threadIdx.x == half * 128) fa_trace(1 + half, it, 0);   // about to wait for scores
       mbar_wait(&sc_full[half], it & 1);
+      if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();
+      uint32_t pd[32];
       if (kCausal && it == n_it - 1)   // key block == query block
-        bwd_elementwise_half<kBf16, false, true, false, false>(tS, tDP, 0u, nl2, nd2, sl2, row, half * 64);
+        dq_elementwise_half<kBf16, true>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd);
       else
-        bwd_elementwise_half<kBf16, false, false, false, false>(tS, tDP, 0u, nl2, nd2, sl2, row, half * 64);
-      tc_wait_st();
-      tc_fence_before();
+        dq_elementwise_half<kBf16, false>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd);
+      if (it > 0) mbar_wait(&ds_free[half], (it - 1) & 1);        // dQ MMAs of the previous block have read the box
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, ch)), "r"(pd[ch * 4]),
+                     "r"(pd[ch * 4 + 1]), "r"(pd[ch * 4 + 2]), "r"(pd[ch * 4 + 3])
+                     : "memory");
+      fence_proxy_async_smem();
       mbar_arrive(&p_full[half]);
+      if (threadIdx.x == half * 128) fa_trace(1 + half, it, 2);   // dS handed over
     }
 
     // epilogue: each warpgroup stores half of the D columns of scale * dQ

@@ -146,11 +146,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int s = j % NS;
         mbar_wait(&k_full[s], (j / NS) & 1);
         tc_fence_after();
-        const uint32_t a0 = qlo + t * kTileLo, b0 = klo + s * kTileLo;
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss_lo(tS(t), a0 + umma_koff_kmajor(k, Cfg::kBoxBytes), b0 + umma_koff_kmajor(k, Cfg::kBoxBytes), idesc_s,
-                     k > 0);
+        const uint32_t a0 = qlo + t * kTileLo, b0 = klo + s * kTileLo, d0 = tS(t);
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+          umma_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
+        });
         tc_commit(&s_full[t]);
         // last tile that reads K block j releases the stage
         const bool last_user = (t == 1) || (nkv[1] <= j);
@@ -167,14 +168,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (j >= nkv[t]) continue;
           mbar_wait(&v_full[s], (j / NS) & 1);
           // P arrives in two 64-key halves so the first half of P·V overlaps the second half of the exponentials
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            mbar_wait(&p_full[t][hf], j & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int k = hf * 4; k < hf * 4 + 4; ++k)
-              umma_ts_lo(tO(t), tS(t) + k * 8, vlo + s * kTileLo + umma_koff_mnmajor(k), idesc_o, (j > 0) || (k > 0));
-          }
+          const uint32_t dO_t = tO(t), aP = tS(t), bV = vlo + s * kTileLo;
+          mbar_wait(&p_full[t][0], j & 1);
+          tc_fence_after();
+          static_for<0, 4>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dO_t, aP, bV, idesc_o, (j > 0) || (k > 0));
+          });
+          mbar_wait(&p_full[t][1], j & 1);
+          tc_fence_after();
+          static_for<4, 8>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dO_t, aP, bV, idesc_o, 1u);
+          });
           tc_commit(&o_full[t]);
           const bool last_user = (t == 1) || (nkv[1] <= j);
           if (last_user) tc_commit(&v_empty[s]);

@@ -10,6 +10,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <type_traits>
 #include <cuda.h>          // CUtensorMap (type only; the encode function is fetched at run time)
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -26,6 +27,28 @@ namespace fa {
 #endif
 #ifndef FA_WATCHDOG_CYCLES
 #define FA_WATCHDOG_CYCLES 4000000000LL
+#endif
+
+// FA_TRACE (debug builds only): CTA (0,0,0) of the kernels appends {event id, clock64} pairs to a device buffer set with
+// fa_debug_set_trace(); used to reconstruct the warp-role timeline.  Compiled out of the production library.
+#ifndef FA_TRACE
+#define FA_TRACE 0
+#endif
+#ifndef FA_TRACE_BLOCK
+#define FA_TRACE_BLOCK 0
+#endif
+#if FA_TRACE
+__device__ long long* g_fa_trace = nullptr;
+__device__ int g_fa_trace_cap = 0;
+// slot = role * 8192 + iteration * 8 + k : plain store, no atomics (an atomic's round trip would distort the timeline)
+__device__ __forceinline__ void fa_trace(int role, int it, int k) {
+  if (g_fa_trace != nullptr && blockIdx.x == FA_TRACE_BLOCK && blockIdx.y == 0 && blockIdx.z == 0) {
+    const int slot = role * 8192 + it * 8 + k;
+    if (slot < g_fa_trace_cap) g_fa_trace[slot] = clock64();
+  }
+}
+#else
+__device__ __forceinline__ void fa_trace(int, int, int) {}
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -238,6 +261,57 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uin
       :
       : "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
       : "memory");
+}
+
+// Issue-loop variants: operand = base low word (kept in one uniform register) + COMPILE-TIME offset, added inside the
+// asm block.  If the additions are visible to the compiler it hoists all of them out of the block loop, runs out of
+// uniform registers and re-materialises every descriptor through R2UR / spills (~40 clk per MMA, measured with
+// tools/trace_dq.py), which made the single issuing thread the bottleneck of the backward kernels.
+template <uint32_t kOffA, uint32_t kOffB>
+__device__ __forceinline__ void umma_ss_off(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 al, %1, %6;\n\t"
+      "add.u32 bl, %2, %7;\n\t"
+      "mov.b64 da, {al, %5};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA), "n"(kOffB)
+      : "memory");
+}
+template <uint32_t kOffA, uint32_t kOffB>
+__device__ __forceinline__ void umma_ts_off(uint32_t tmem_d, uint32_t tmem_a_base, uint32_t b_base, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 ta, bl;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 ta, %1, %6;\n\t"
+      "add.u32 bl, %2, %7;\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA),
+        "n"(kOffB)
+      : "memory");
+}
+// compile-time loop: f(std::integral_constant<int, I>) for I in [0, N)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
 }
 
 // Instruction descriptor for kind::f16 (fp16/bf16 inputs, fp32 accumulate).
