@@ -94,7 +94,7 @@ def _declare(lib):
     lib.fa_bwd_preprocess.restype = i
     lib.fa_bwd_preprocess.argtypes = [vp, vp, vp, i, i, i, i, st, st, i, vp]
     lib.fa_bwd_workspace_bytes.restype = sz
-    lib.fa_bwd_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.fa_bwd_workspace_bytes.argtypes = [i, i, i, i, i, i, i]
     lib.fa_bwd.restype = i
     lib.fa_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i, vp]
     lib.fa_bwd_partial.restype = i

@@ -90,13 +90,14 @@ def backward_preprocess(O: torch.Tensor, dO: torch.Tensor) -> torch.Tensor:
     return delta
 
 
-BWD_DKDV, BWD_DQ = 1, 2
+BWD_DKDV, BWD_DQ, BWD_FUSED = 1, 2, 4
 
 
-def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int = BWD_DKDV | BWD_DQ, delta=None):
+def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int | None = None, delta=None):
     """dQ, dK, dV (B,H,N,d) in the input dtype; deterministic (bit-identical across runs).
-    `which` selects the dK/dV kernel, the dQ kernel or both (fa_bwd_partial); unselected outputs are uninitialised.
-    `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch."""
+    `which` = None runs what fa_bwd runs: the two-kernel path (BWD_DKDV | BWD_DQ; either half can be selected alone,
+    unselected outputs are uninitialised).  BWD_FUSED selects the single-pass kernel with the ordered dQ reduction
+    (16-bit inputs only).  `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
@@ -108,7 +109,11 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int =
     dQ = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
     dK = torch.empty_like(dQ)
     dV = torch.empty_like(dQ)
-    ws_bytes = lib.fa_bwd_workspace_bytes(B, H, N, d_run, code)
+    if which is None:
+        which = BWD_DKDV | BWD_DQ
+    ws_bytes = lib.fa_bwd_workspace_bytes(B, H, N, d_run, code, int(bool(causal)), int(which))
+    # scratch of the ordered dQ reduction, owned by the caching allocator like every other buffer (the reference
+    # allocates its dQ lock buffers the same way, flash_attention_torch.py:107-109)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=Q.device) if ws_bytes else None
     with torch.cuda.device(Q.device):
         rc = lib.fa_bwd_partial(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(lse), _ptr(delta), _ptr(dQ), _ptr(dK),

@@ -2,6 +2,7 @@
 // encoding and kernel launches.  No torch types, no device allocation, no synchronisation.
 #include "../../include/fa_b200.h"
 
+#include "fa_bwd_fused_sm100.cuh"
 #include "fa_bwd_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
 #include "fa_preprocess.cuh"
@@ -133,6 +134,47 @@ int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaSt
   return 0;
 }
 
+// Workspace of the fused backward: [ticket | pad to 256 B][turn counters 2 x tiles, padded to 256 B][fp32 dQ tiles A][B]
+struct FusedLayout {
+  size_t ctrl_bytes, acc_floats, total_bytes;
+  int n_blocks;
+  long long tiles;
+};
+FusedLayout fused_layout(int B, int H, int N, int D, int causal) {
+  FusedLayout L{};
+  L.n_blocks = (N + 127) / 128;
+  L.tiles = (long long)B * H * L.n_blocks;
+  L.ctrl_bytes = 256 + (((size_t)L.tiles * 2 * sizeof(int) + 255) & ~(size_t)255);
+  L.acc_floats = (size_t)L.tiles * 128 * D;
+  L.total_bytes = L.ctrl_bytes + L.acc_floats * sizeof(float) * (causal ? 1 : 2);
+  return L;
+}
+
+template <bool kBf16, int kD, bool kCausal>
+int launch_bwd16_fused(const fa::BwdMaps& m, const fa::BwdParams& p, void* workspace, cudaStream_t st) {
+  const FusedLayout L = fused_layout(p.B, p.H, p.N, kD, kCausal);
+  fa::FusedParams fp{};
+  fp.base = p;
+  char* ws = static_cast<char*>(workspace);
+  fp.ticket = reinterpret_cast<int*>(ws);
+  fp.sem = reinterpret_cast<int*>(ws + 256);
+  fp.dq_acc = reinterpret_cast<float*>(ws + L.ctrl_bytes);
+  fp.acc_b_off = kCausal ? 0 : (long long)L.acc_floats;
+  fp.n_blocks = L.n_blocks;
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.ctrl_bytes, st);
+  if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(fused) cudaMemsetAsync");
+  auto kern = fa::fa_bwd_fused_kernel<kBf16, kD, kCausal>;
+  if (int r = set_smem(kern, fa::FusedCfg<kD>::kSmemBytes)) return r;
+  kern<<<(unsigned)L.tiles, fa::FusedCfg<kD>::kThreads, fa::FusedCfg<kD>::kSmemBytes, st>>>(m.q, m.k, m.v, m.dout, fp);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(fused) launch");
+  dim3 grid(L.n_blocks, p.H, p.B);
+  fa::fa_bwd_dq_convert_kernel<kBf16, kD><<<grid, 256, 0, st>>>(fp.dq_acc, fp.acc_b_off, p.dq, p.dq_s[0], p.dq_s[1],
+                                                               p.dq_s[2], p.H, p.N, L.n_blocks, p.scale);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "fa_bwd(dQ convert) launch");
+}
+
 }  // namespace
 
 #if FA_TRACE
@@ -147,7 +189,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 1; }
+int fa_version(void) { return 2; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -237,9 +279,11 @@ int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int 
   return fail(-3, "fa_bwd_preprocess: no kernel for dtype %d D %d", dtype, D);
 }
 
-size_t fa_bwd_workspace_bytes(int B, int H, int N, int D, int dtype) {
-  (void)B, (void)H, (void)N, (void)D, (void)dtype;
-  return 0;  // the two-kernel backward needs no scratch: every gradient tile has a single owner CTA
+size_t fa_bwd_workspace_bytes(int B, int H, int N, int D, int dtype, int causal, int which) {
+  if (B <= 0 || H <= 0 || N <= 0 || D <= 0) return 0;
+  // the two-kernel backward needs no scratch: every gradient tile has a single owner CTA
+  if (which != FA_BWD_FUSED || dtype == FA_DTYPE_F32) return 0;
+  return fused_layout(B, H, N, D, causal).total_bytes;
 }
 
 int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
@@ -247,6 +291,8 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t do_strides[4], const int64_t dq_strides[4], const int64_t dk_strides[4],
            const int64_t dv_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
+  // The two-kernel path (every gradient tile has one owner CTA, no workspace) is the default: on B200 it is faster than
+  // the single-pass kernel, whose dQ reduction is bound by the SM -> L2 path.
   return fa_bwd_partial(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, D, q_strides,
                         k_strides, v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale,
                         causal, FA_BWD_DKDV | FA_BWD_DQ, stream);
@@ -259,9 +305,16 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, void* stream) {
   g_err[0] = 0;
-  if ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ)))
-    return fail(-10, "fa_bwd_partial: which must be a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
-  (void)workspace, (void)workspace_bytes;
+  if (which != FA_BWD_FUSED && ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ))))
+    return fail(-10, "fa_bwd_partial: which must be FA_BWD_FUSED or a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
+  if (which == FA_BWD_FUSED) {
+    if (dtype == FA_DTYPE_F32) return fail(-10, "fa_bwd_partial: FA_BWD_FUSED is a 16-bit kernel; float32 uses FA_BWD_DKDV | FA_BWD_DQ");
+    const size_t need = fa_bwd_workspace_bytes(B, H, N, D, dtype, causal, FA_BWD_FUSED);
+    if (!workspace || workspace_bytes < need)
+      return fail(-11, "fa_bwd: workspace of %zu bytes required (got %zu); size it with fa_bwd_workspace_bytes", need,
+                  workspace ? workspace_bytes : (size_t)0);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(-8, "fa_bwd: workspace must be 256-byte aligned");
+  }
   if (int r = check_common("fa_bwd", B, H, N, D, dtype, softmax_scale)) return r;
   if (!q_strides || !k_strides || !v_strides || !do_strides || !dq_strides || !dk_strides || !dv_strides)
     return fail(-6, "fa_bwd: null stride array");
@@ -307,8 +360,10 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   p.B = B, p.H = H, p.N = N;
   fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
   p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e;
-#define FA_BWD_CASE(BF, DD, C) \
-  if (bf == BF && D == DD && (causal != 0) == C) return launch_bwd16<BF, DD, C>(m, p, which, st);
+#define FA_BWD_CASE(BF, DD, C)                                                                  \
+  if (bf == BF && D == DD && (causal != 0) == C)                                                \
+    return which == FA_BWD_FUSED ? launch_bwd16_fused<BF, DD, C>(m, p, workspace, st)           \
+                                 : launch_bwd16<BF, DD, C>(m, p, which, st);
   FA_BWD_CASE(true, 128, true)
   FA_BWD_CASE(true, 128, false)
   FA_BWD_CASE(true, 64, true)

@@ -48,10 +48,14 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
 int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int H, int N, int D,
                       const int64_t o_strides[4], const int64_t do_strides[4], int dtype, void* stream);
 
-/* Bytes of scratch fa_bwd needs for this problem (may be 0). */
-size_t fa_bwd_workspace_bytes(int B, int H, int N, int D, int dtype);
+/* Bytes of 256-byte aligned scratch fa_bwd_partial needs for this problem and choice of kernels (`which`, below):
+ * 0 for the two-kernel path and for float32; for FA_BWD_FUSED the fp32 dQ partial sums and turn counters of its
+ * ordered dQ reduction (the library zeroes what needs zeroing).  The reference allocates its backward scratch — the dQ
+ * lock / flag buffers — in the same place: flash_attention_torch.py:107-109,247, flash_attention_wrappers.py:104-108,123. */
+size_t fa_bwd_workspace_bytes(int B, int H, int N, int D, int dtype, int causal, int which);
 
 /* Backward pass: dQ, dK, dV from Q, K, V, dO, lse, delta.  Deterministic: bit-identical across runs.
+ * Runs the two-kernel path (FA_BWD_DKDV | FA_BWD_DQ below); `workspace` may be NULL.
  * Replaces bwd_kernel / bwd_deterministic_kernel launches at flash_attention_torch.py:136-154,274-292 and
  * flash_attention_wrappers.py:122-174. */
 int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
@@ -60,13 +64,17 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
            const int64_t do_strides[4], const int64_t dq_strides[4], const int64_t dk_strides[4],
            const int64_t dv_strides[4], int dtype, float softmax_scale, int causal, void* stream);
 
-/* One half of fa_bwd at a time: `which` = FA_BWD_DKDV (the dK/dV kernel, owner = key block), FA_BWD_DQ (the dQ
- * kernel, owner = query block) or both.  The reference has a single backward launch (flash_attention_torch.py:136-154)
+/* Backward with an explicit choice of kernels.  `which` = FA_BWD_DKDV (the dK/dV kernel, owner = key block), FA_BWD_DQ
+ * (the dQ kernel, owner = query block, recomputes S and dP) or both — what fa_bwd runs; or FA_BWD_FUSED (16-bit dtypes
+ * only): one pass like the reference's bwd_kernel, five matmuls per block pair instead of seven, with dQ accumulated
+ * across key blocks by an ORDERED reduction in `workspace` (a turn counter per tile instead of the reference's spin lock,
+ * flash_attention_kernels.py:305-320), deterministic as well.  The reference has a single backward launch (flash_attention_torch.py:136-154)
  * whose dQ part is the spin-locked read-modify-write of flash_attention_kernels.py:305-320; here the two parts are
  * separate kernels, exposed for callers that need only some gradients and for per-kernel timing.  Outputs not
  * selected are left untouched (their pointers must still be valid). */
 #define FA_BWD_DKDV 1
 #define FA_BWD_DQ 2
+#define FA_BWD_FUSED 4
 int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
                    const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
                    int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],

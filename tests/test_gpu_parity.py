@@ -388,3 +388,39 @@ def test_host_pipeline_matches_resident_path_bitwise():
     assert torch.equal(O3, flash_attention_forward(Q, K, V, DEV, False, 0.09)[0].cpu())
     with pytest.raises(ValueError):
         attention_from_host(Q, K, V)
+
+
+# ------------------------------------------------------------------------------------------------ backward variants
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("N", [128, 200, 640, 1536])
+def test_two_kernel_backward_matches_oracle_and_fused(dtype, D, causal, N):
+    """The two backward implementations — fa_bwd's two-kernel path and the single-pass kernel with the ordered dQ
+    reduction (FA_BWD_FUSED) — against the oracle.  Under the causal mask both visit the query blocks of a key block in
+    the same order, so dK and dV agree bit for bit."""
+    B, H, scale = 2, 3, 1.0 / math.sqrt(D)
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(11, B, H, N, D, dtype))
+    O, L = flash_attention_forward(Q, K, V, DEV, causal, scale)
+    two = _native.backward(Q, K, V, O, dO, L, causal, scale, which=_native.BWD_DKDV | _native.BWD_DQ)
+    one = _native.backward(Q, K, V, O, dO, L, causal, scale, which=_native.BWD_FUSED)
+    torch.cuda.synchronize()
+    ref = orc.attention_grads_fp64(Q.cpu().float(), K.cpu().float(), V.cpu().float(), dO.cpu().float(), scale, causal)
+    for name, a, b in zip(("dQ", "dK", "dV"), two, one):
+        assert rel_err(a.cpu(), ref[name]) <= 1e-2, name
+        assert rel_err(b.cpu(), ref[name]) <= 1e-2, name
+    if causal:
+        assert torch.equal(two[1], one[1]) and torch.equal(two[2], one[2])
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_variants_bit_identical_many_heads(causal):
+    """Ordered dQ reduction: more CTAs than SMs, so turn-taking between waves is exercised; 5 runs must agree bitwise."""
+    B, H, N, D = 2, 24, 1024, 128
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(3, B, H, N, D, torch.bfloat16))
+    O, L = flash_attention_forward(Q, K, V, DEV, causal, 0.09)
+    for which in (_native.BWD_FUSED, _native.BWD_DKDV | _native.BWD_DQ):
+        first = _native.backward(Q, K, V, O, dO, L, causal, 0.09, which=which)
+        for _ in range(4):
+            again = _native.backward(Q, K, V, O, dO, L, causal, 0.09, which=which)
+            for a, b in zip(first, again):
+                assert torch.equal(a, b)

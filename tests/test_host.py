@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 1
+    assert lib.fa_version() == 2
     assert isinstance(lib.fa_last_error(), bytes)
 
 
@@ -42,7 +42,14 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     # non-positive scale
     assert lib.fa_fwd(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 0.0, 0, null) < 0
     assert lib.fa_bwd_preprocess(null, null, null, 1, 1, 128, 64, s, s, 1, null) < 0
-    assert lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1) == 0
+    # two-kernel path (what fa_bwd runs): no scratch; single-pass kernel: fp32 dQ tiles + turn counters
+    assert lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1, 1, 3) == 0
+    assert lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 2, 1, 4) == 0
+    causal = lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1, 1, 4)
+    full = lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1, 0, 4)
+    tiles = 2 * 32 * 64
+    assert causal == 256 + tiles * 8 + tiles * 128 * 128 * 4
+    assert full == 256 + tiles * 8 + 2 * tiles * 128 * 128 * 4
     with pytest.raises(_lib.FlashAttentionLibraryError):
         _lib.check(-1, "fa_fwd")
 

@@ -1,8 +1,8 @@
 #!/bin/bash
 # fast iteration: 16-bit parity subset + bench without the CPU leg
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x --timeout 300 -k "16bit or config or bit_identical or head_slice or autograd" > gpurun_out/pytest_iter.log 2>&1
-echo "pytest exit=$?" >> gpurun_out/pytest_iter.log; tail -4 gpurun_out/pytest_iter.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x --timeout 300 -k "${1:-16bit or config2 or config3 or bit_identical or head_slice or autograd or two_kernel}" > gpurun_out/pytest_iter.log 2>&1
+echo "pytest exit=$?" >> gpurun_out/pytest_iter.log; tail -15 gpurun_out/pytest_iter.log
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_iter.log 2> gpurun_out/bench_iter.err; echo "bench exit=$?"
 python - <<'PY'
 import json

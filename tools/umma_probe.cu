@@ -18,6 +18,7 @@ using namespace fa;
 
 struct ProbeParams {
   int a_tmem;    // 0: A from smem (K-major), 1: A from TMEM
+  int a_mn;      // A from smem stored [K x 128] (MN-major): the dS operand of the fused backward's dQ product
   int b_mn;      // 0: B is [N x K] (K-major), 1: B is [K x N] (MN-major)
   int N, K;      // N in {64,128}, K in {64,128}
   int is_bf16;
@@ -55,10 +56,14 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     uint32_t bytes = b_boxes * b_rows * 128;
-    if (!p.a_tmem) bytes += a_boxes * 128 * 128;
+    if (!p.a_tmem) bytes += p.K * 128 * 2;
     mbar_arrive_expect_tx(&bar_load, bytes);
-    if (!p.a_tmem)
-      for (int b = 0; b < a_boxes; ++b) tma_load_4d(sA + b * 16384, &tmA, &bar_load, b * 64, 0, 0, 0);
+    if (!p.a_tmem) {
+      if (p.a_mn)   // [K rows x 128 columns]: two boxes of K rows x 64 columns
+        for (int b = 0; b < 2; ++b) tma_load_4d(sA + b * p.K * 128, &tmA, &bar_load, b * 64, 0, 0, 0);
+      else
+        for (int b = 0; b < a_boxes; ++b) tma_load_4d(sA + b * 16384, &tmA, &bar_load, b * 64, 0, 0, 0);
+    }
     for (int b = 0; b < b_boxes; ++b) tma_load_4d(sB + b * b_rows * 128, &tmB, &bar_load, b * 64, 0, 0, 0);
   }
   if (p.a_tmem) {
@@ -83,7 +88,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_wait(&bar_load, 0);
     tc_fence_after();
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(p.is_bf16, 128, p.N, 0, p.b_mn);
+      const uint32_t idesc = umma_idesc_f16(p.is_bf16, 128, p.N, p.a_mn, p.b_mn);
       for (int k = 0; k < p.K / 16; ++k) {
         uint64_t db;
         if (p.b_mn)
@@ -93,7 +98,8 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.a_tmem) {
           umma_ts(tmem_D, tmem_A + k * 8, db, idesc, k > 0);
         } else {
-          uint64_t da = umma_desc_kmajor(smem_u32(sA) + (k / 4) * 16384, k % 4);
+          uint64_t da = p.a_mn ? umma_desc_mnmajor(smem_u32(sA), (uint32_t)p.K * 128u, k)
+                               : umma_desc_kmajor(smem_u32(sA) + (k / 4) * 16384, k % 4);
           umma_ss(tmem_D, da, db, idesc, k > 0);
         }
       }
@@ -145,11 +151,13 @@ static double run_case(const ProbeParams& p, const char* name) {
   std::vector<uint16_t> hA(M * K), hB(N * K);
   std::vector<float> fA(M * K), fB(N * K);
   srand(1234 + N * 7 + K * 3 + p.a_tmem * 11 + p.b_mn * 5);
-  for (int i = 0; i < M * K; ++i) {
-    float v = (float)(rand() % 2001 - 1000) / 500.0f;
-    hA[i] = f2bf(v);
-    fA[i] = bf2f(hA[i]);
-  }
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) {
+      float v = (float)(rand() % 2001 - 1000) / 500.0f;
+      uint16_t h = f2bf(v);
+      hA[p.a_mn ? k * M + m : m * K + k] = h;
+      fA[m * K + k] = bf2f(h);
+    }
   // B logical: Bmat[n][k]; storage is [N x K] (K-major) or [K x N] (MN-major)
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
@@ -171,7 +179,8 @@ static double run_case(const ProbeParams& p, const char* name) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xff, M * N * 4));
   CUtensorMap tmA, tmB;
-  int r1 = make_tmap_bhnd_16bit(&tmA, dA, 1, 1, 1, M, K, (int64_t)M * K, (int64_t)M * K, K, 128);
+  int r1 = p.a_mn ? make_tmap_bhnd_16bit(&tmA, dA, 1, 1, 1, K, M, (int64_t)M * K, (int64_t)M * K, M, K)
+                  : make_tmap_bhnd_16bit(&tmA, dA, 1, 1, 1, M, K, (int64_t)M * K, (int64_t)M * K, K, 128);
   int r2 = p.b_mn ? make_tmap_bhnd_16bit(&tmB, dB, 1, 1, 1, K, N, (int64_t)K * N, (int64_t)K * N, N, K)
                   : make_tmap_bhnd_16bit(&tmB, dB, 1, 1, 1, N, K, (int64_t)N * K, (int64_t)N * K, K, N);
   if (r1 || r2) {
@@ -226,6 +235,10 @@ int main() {
       p.a_tmem = 1;
       double e2 = run_case(p, "TS  A TMEM,         B MN-major (expected)");
       fails += (e1 > 1e-2) + (e2 > 1e-2);
+      // MN-major A from shared memory (dQ = dS K in the fused backward: both operands indexed by key row)
+      p.a_tmem = 0; p.a_mn = 1;
+      fails += run_case(p, "SS  A MN-major smem, B MN-major") > 1e-2;
+      p.a_mn = 0;
       if (e1 > 1e-2) {
         // diagnostics only: alternative readings of the LBO/SBO fields
         p.a_tmem = 0;
