@@ -138,6 +138,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # the reference's CPU path with every host thread it can use (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    torch.set_num_threads(os.cpu_count() or 1)
     w = WORKLOAD
     scale = 1.0 / w["D"] ** 0.5
     heads = 2
@@ -314,7 +316,8 @@ def run_ours(args):
            "pcie_gbs_each_way": io_bytes / (e_ms * 1e-3) / 1e9}
 
     if rank == 0:
-        cpu = cpu_baseline() if not args.no_cpu_baseline else None
+        # on rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1 on multi-rank launches; the N = 1 line carries it)
+        cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -22,6 +22,17 @@
 
 #include "sm100_ptx.cuh"
 
+// Which of every 8 consecutive column pairs compute exp2 with the FMA-pipe polynomial instead of MUFU (bit i = pair i).
+// Measured on B200 (tools/fwd_probe.py): D = 128 is bound by the S -> softmax -> P.V dependency chain, a quarter of the
+// exponentials off MUFU gives +2 %; D = 64 (half the tensor work per exponential) gains 10 % with three in eight;
+// one in two is slower everywhere (issue-slot bound).
+#ifndef FA_FWD_POLY_MASK_D128
+#define FA_FWD_POLY_MASK_D128 0x88
+#endif
+#ifndef FA_FWD_POLY_MASK_D64
+#define FA_FWD_POLY_MASK_D64 0x92
+#endif
+
 namespace fa {
 
 struct FwdParams {
@@ -275,7 +286,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const uint64_t x2 = f32x2_fma(f32x2_pack_bits(sr[c * 32 + 2 * i], sr[c * 32 + 2 * i + 1]), sl2_2, nm2);
           float x0, x1;
           f32x2_unpack(x2, x0, x1);
-          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          float p0, p1;
+          if (((kD == 64 ? FA_FWD_POLY_MASK_D64 : FA_FWD_POLY_MASK_D128) >> (i & 7)) & 1) {   // FMA-pipe exp2
+            ex2_poly_x2(x0, x1, p0, p1);
+          } else {
+            p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          }
           ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));
           pk[i] = pack2<kBf16>(p0, p1);
         }

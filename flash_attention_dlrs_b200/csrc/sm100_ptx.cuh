@@ -453,6 +453,28 @@ __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// exp2 of two fp32 values on the FMA pipe (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5, 2^f by a degree-3 minimax
+// polynomial (max relative error 7.5e-5, below the half-ulp of the 16-bit P it feeds), 2^n by adding n to the exponent
+// field.  The MUFU unit does 4 ex2 per clock per SM sub-partition and is the tightest unit of the softmax stage;
+// moving a share of the exponentials here balances it against the issue slots.  Valid for x <= 126; x is clamped at
+// -125 (masked scores are -inf).
+__device__ __forceinline__ void ex2_poly_x2(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  const uint64_t x = f32x2_pack(x0, x1);
+  const uint64_t t = f32x2_add(x, f32x2_pack(12582912.f, 12582912.f));          // 1.5 * 2^23: low mantissa bits = n
+  const uint64_t n = f32x2_add(t, f32x2_pack(-12582912.f, -12582912.f));
+  const uint64_t f = f32x2_fma(n, f32x2_pack(-1.f, -1.f), x);
+  uint64_t q = f32x2_fma(f32x2_pack(0.05517164617776871f, 0.05517164617776871f), f,
+                         f32x2_pack(0.2426111251115799f, 0.2426111251115799f));
+  q = f32x2_fma(q, f, f32x2_pack(0.6932609677314758f, 0.6932609677314758f));
+  q = f32x2_fma(q, f, f32x2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  f32x2_unpack(q, q0, q1);
+  f32x2_unpack(t, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
 // 16-byte shared-memory load as two packed fp32 pairs (explicit .shared so the compiler does not fall back to
 // generic loads when the pointer's address space is not provable)
 __device__ __forceinline__ void lds_f32x2x2(uint32_t saddr, uint64_t& a, uint64_t& b) {
