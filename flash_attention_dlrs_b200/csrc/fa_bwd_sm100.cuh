@@ -24,6 +24,13 @@
 
 #include "sm100_ptx.cuh"
 
+// Share of the exponentials computed on the FMA pipe instead of MUFU (bit i = column pair i of every 8).  Off: the
+// backward kernels are bound by the TMEM round trips of their elementwise stage, not by MUFU (tools/bwd_probe.py: no gain
+// at 1/4, slower at 1/2).
+#ifndef FA_BWD_POLY_MASK
+#define FA_BWD_POLY_MASK 0x00
+#endif
+
 namespace fa {
 
 struct BwdMaps {
@@ -119,7 +126,12 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
 #endif
         float x0, x1;
         f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl4[u]), x0, x1);
-        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        float p0, p1;
+        if ((FA_BWD_POLY_MASK >> (g & 7)) & 1) {   // FMA-pipe exp2 for a share of the pairs (see fa_fwd_sm100.cuh)
+          ex2_poly_x2(x0, x1, p0, p1);
+        } else {
+          p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        }
         if constexpr (kMask) {
           // keep key <= query.  Transposed scores: row = key, column = query; otherwise row = query, column = key.
           const int c0 = col0 + e;
@@ -170,7 +182,12 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
 #endif
     float x0, x1;
     f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl), x0, x1);
-    float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+    float p0, p1;
+    if ((FA_BWD_POLY_MASK >> (g & 7)) & 1) {
+      ex2_poly_x2(x0, x1, p0, p1);
+    } else {
+      p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+    }
     if constexpr (kMask) {   // causal diagonal block: keep key <= query (row = query, column = key)
       const int c0 = col0 + e;
       if (c0 > row) p0 = 0.f;
