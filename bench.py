@@ -54,6 +54,28 @@ def load_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_dram_bytes(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on the bench workload, from the committed
+    `ncu --set full` capture (profiles/r01_full_summary.csv, tools/gpu_prof.sh); None if the capture is absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_full_summary.csv")
+    name = {"fwd": "fa_fwd_kernel", "bwd_dkdv": "fa_bwd_dkdv_kernel", "bwd_dq": "fa_bwd_dq_kernel"}.get(kernel)
+    if name is None or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rows = list(csv.reader(f))
+    hdr, units = rows[0], rows[1]
+    try:
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if name in r[0]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    except (ValueError, KeyError, IndexError):
+        return None
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -253,7 +275,7 @@ def run_ours(args):
     dominant = max(("fwd", "bwd_dkdv", "bwd_dq"), key=lambda k: k_ms[k])
     ach = k_alg[dominant] / (k_ms[dominant] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dominant, "achieved": ach, "peak": peaks["burst"], "unit": "TFLOP/s",
-                "frac": ach / peaks["burst"], "traffic": None,
+                "frac": ach / peaks["burst"], "traffic": ncu_dram_bytes(dominant),
                 "peak_source": peaks["source"] + ", burst bf16 (kernel timed alone)",
                 "hw_tflops_incl_recompute": k_hw[dominant] / (k_ms[dominant] * 1e-3) / 1e12}
     pre_bytes = 2.0 * B * H * N * D * 2 + 4.0 * B * H * N

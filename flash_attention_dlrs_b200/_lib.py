@@ -19,7 +19,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = Path(os.environ["FA_B200_LIB"]) if os.environ.get("FA_B200_LIB") else PKG_DIR / "libfa_b200.so"
 HEADER = REPO_ROOT / "include" / "fa_b200.h"
 
-FA_DTYPE_F16, FA_DTYPE_BF16, FA_DTYPE_F32 = 0, 1, 2
+FA_DTYPE_F16, FA_DTYPE_BF16, FA_DTYPE_F32, FA_DTYPE_F8E4M3, FA_DTYPE_F8E5M2 = 0, 1, 2, 3, 4
 
 # every symbol include/fa_b200.h declares
 EXPORTED_SYMBOLS = (

@@ -12,7 +12,10 @@ import torch
 
 from . import _lib
 
-_DTYPES = {torch.float16: _lib.FA_DTYPE_F16, torch.bfloat16: _lib.FA_DTYPE_BF16, torch.float32: _lib.FA_DTYPE_F32}
+_DTYPES = {torch.float16: _lib.FA_DTYPE_F16, torch.bfloat16: _lib.FA_DTYPE_BF16, torch.float32: _lib.FA_DTYPE_F32,
+           # forward only; float8_e5m2 is the FP8 type of the reference's dtype map (flash_attention_torch.py:15-16)
+           torch.float8_e5m2: _lib.FA_DTYPE_F8E5M2, torch.float8_e4m3fn: _lib.FA_DTYPE_F8E4M3}
+FP8_DTYPES = (torch.float8_e5m2, torch.float8_e4m3fn)
 MAX_HEAD_DIM = 128
 
 
@@ -30,6 +33,8 @@ def padded_head_dim(d: int, dtype: torch.dtype) -> int:
         raise ValueError(f"head size d={d} not supported (1 <= d <= {MAX_HEAD_DIM})")
     if dtype == torch.float32:
         return max(1 << (d - 1).bit_length(), 16)
+    if dtype in FP8_DTYPES:
+        return 128   # one 128-byte TMA box per row
     return 64 if d <= 64 else 128
 
 
@@ -48,6 +53,10 @@ def _pad_d(t: torch.Tensor, d_run: int) -> torch.Tensor:
     d = t.shape[-1]
     if d == d_run:
         return t
+    if t.dtype in FP8_DTYPES:   # F.pad has no FP8 kernel; the all-zero byte is +0.0 in both formats
+        out = torch.zeros((*t.shape[:-1], d_run), dtype=torch.uint8, device=t.device)
+        out[..., :d] = t.view(torch.uint8)
+        return out.view(t.dtype)
     return torch.nn.functional.pad(t, (0, d_run - d), mode="constant", value=0.0)
 
 
@@ -101,6 +110,8 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
+    if Q.dtype in FP8_DTYPES:
+        raise TypeError(f"dtype {Q.dtype} not supported in backward (the FP8 path is forward-only).")
     d_run = padded_head_dim(d, Q.dtype)
     q, k, v, o, do = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V, O, dO))
     lse = L.reshape(B, H, N).to(torch.float32).contiguous()

@@ -33,9 +33,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 int check_common(const char* fn, int B, int H, int N, int D, int dtype, float scale) {
   if (B <= 0 || H <= 0 || N <= 0 || D <= 0) return fail(-1, "%s: B, H, N, D must be positive (got %d,%d,%d,%d)", fn, B, H, N, D);
-  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F32)
-    return fail(-2, "%s: dtype %d not supported (0 = f16, 1 = bf16, 2 = f32)", fn, dtype);
-  if (dtype == FA_DTYPE_F32) {
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_F8E4M3 &&
+      dtype != FA_DTYPE_F8E5M2)
+    return fail(-2, "%s: dtype %d not supported (0 = f16, 1 = bf16, 2 = f32, 3 = f8e4m3, 4 = f8e5m2)", fn, dtype);
+  if (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2) {
+    if (D != 128) return fail(-3, "%s: FP8 head size must be 128 (got %d); pad in the caller", fn, D);
+  } else if (dtype == FA_DTYPE_F32) {
     if (!(D == 16 || D == 32 || D == 64 || D == 128))
       return fail(-3, "%s: float32 head size must be 16, 32, 64 or 128 (got %d); pad in the caller", fn, D);
   } else if (!(D == 64 || D == 128)) {
@@ -48,7 +51,7 @@ int check_common(const char* fn, int B, int H, int N, int D, int dtype, float sc
 int check_tensor(const char* fn, const char* name, const void* p, const int64_t s[4], int dtype, int B, int H) {
   if (!p) return fail(-6, "%s: %s is null", fn, name);
   if (s[3] != 1) return fail(-7, "%s: %s last-dim stride must be 1 (got %lld)", fn, name, (long long)s[3]);
-  const int64_t gran = (dtype == FA_DTYPE_F32) ? 4 : 8;  // 16 bytes
+  const int64_t gran = (dtype == FA_DTYPE_F32) ? 4 : (dtype >= FA_DTYPE_F8E4M3 ? 16 : 8);  // 16 bytes
   if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) return fail(-8, "%s: %s must be 16-byte aligned", fn, name);
   if (s[2] % gran != 0 || (H > 1 && s[1] % gran != 0) || (B > 1 && s[0] % gran != 0))
     return fail(-9, "%s: %s strides must be multiples of 16 bytes", fn, name);
@@ -67,13 +70,14 @@ void fill3(int64_t (&dst)[3], const int64_t s[4]) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <bool kBf16, int kD, bool kCausal>
+template <int kElt, int kD, bool kCausal>
 int launch_fwd16(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p, int H,
                  int B, cudaStream_t st) {
-  auto kern = fa::fa_fwd_kernel<kBf16, kD, kCausal>;
-  if (int r = set_smem(kern, fa::FwdCfg<kD>::kSmemBytes)) return r;
+  using Cfg = fa::FwdCfg<kD, kElt>;
+  auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal>;
+  if (int r = set_smem(kern, Cfg::kSmemBytes)) return r;
   dim3 grid(p.q_blocks, H, B);
-  kern<<<grid, fa::FwdCfg<kD>::kThreads, fa::FwdCfg<kD>::kSmemBytes, st>>>(tq, tk, tv, p);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd launch");
 }
@@ -222,28 +226,34 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
   }
 
   const int bf = dtype == FA_DTYPE_BF16;
+  const bool f8 = dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2;
   CUtensorMap tq, tk, tv;
-  if (int r = fa::make_tmap_bhnd_16bit(&tq, q, bf, B, H, N, D, q_strides[0], q_strides[1], q_strides[2], 128))
-    return fail(r, "fa_fwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
-  if (int r = fa::make_tmap_bhnd_16bit(&tk, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 128))
-    return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
-  if (int r = fa::make_tmap_bhnd_16bit(&tv, v, bf, B, H, N, D, v_strides[0], v_strides[1], v_strides[2], 128))
-    return fail(r, "fa_fwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
+  auto encode = [&](CUtensorMap* m, const void* ptr, const int64_t* st4) {
+    return f8 ? fa::make_tmap_bhnd_8bit(m, ptr, B, H, N, D, st4[0], st4[1], st4[2], 128)
+              : fa::make_tmap_bhnd_16bit(m, ptr, bf, B, H, N, D, st4[0], st4[1], st4[2], 128);
+  };
+  if (int r = encode(&tq, q, q_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
+  if (int r = encode(&tk, k, k_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
+  if (int r = encode(&tv, v, v_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
   fa::FwdParams p{};
   p.o = o, p.lse = lse, p.B = B, p.H = H, p.N = N;
   p.o_sB = o_strides[0], p.o_sH = o_strides[1], p.o_sN = o_strides[2];
   p.scale_log2 = softmax_scale * kLog2e;
   p.q_blocks = (N + 255) / 256;
-#define FA_FWD_CASE(BF, DD, C) \
-  if (bf == BF && D == DD && (causal != 0) == C) return launch_fwd16<BF, DD, C>(tq, tk, tv, p, H, B, st);
-  FA_FWD_CASE(true, 128, true)
-  FA_FWD_CASE(true, 128, false)
-  FA_FWD_CASE(true, 64, true)
-  FA_FWD_CASE(true, 64, false)
-  FA_FWD_CASE(false, 128, true)
-  FA_FWD_CASE(false, 128, false)
-  FA_FWD_CASE(false, 64, true)
-  FA_FWD_CASE(false, 64, false)
+#define FA_FWD_CASE(E, DD, C) \
+  if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
+  FA_FWD_CASE(FA_DTYPE_BF16, 128, true)
+  FA_FWD_CASE(FA_DTYPE_BF16, 128, false)
+  FA_FWD_CASE(FA_DTYPE_BF16, 64, true)
+  FA_FWD_CASE(FA_DTYPE_BF16, 64, false)
+  FA_FWD_CASE(FA_DTYPE_F16, 128, true)
+  FA_FWD_CASE(FA_DTYPE_F16, 128, false)
+  FA_FWD_CASE(FA_DTYPE_F16, 64, true)
+  FA_FWD_CASE(FA_DTYPE_F16, 64, false)
+  FA_FWD_CASE(FA_DTYPE_F8E4M3, 128, true)
+  FA_FWD_CASE(FA_DTYPE_F8E4M3, 128, false)
+  FA_FWD_CASE(FA_DTYPE_F8E5M2, 128, true)
+  FA_FWD_CASE(FA_DTYPE_F8E5M2, 128, false)
 #undef FA_FWD_CASE
   return fail(-3, "fa_fwd: no kernel for dtype %d D %d", dtype, D);
 }
@@ -251,6 +261,8 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
 int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int H, int N, int D,
                       const int64_t o_strides[4], const int64_t do_strides[4], int dtype, void* stream) {
   g_err[0] = 0;
+  if (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2)
+    return fail(-2, "fa_bwd_preprocess: FP8 is forward-only (dtype %d)", dtype);
   if (int r = check_common("fa_bwd_preprocess", B, H, N, D, dtype, 1.0f)) return r;
   if (!o_strides || !do_strides) return fail(-6, "fa_bwd_preprocess: null stride array");
   if (int r = check_tensor("fa_bwd_preprocess", "o", o, o_strides, dtype, B, H)) return r;
@@ -315,6 +327,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                   workspace ? workspace_bytes : (size_t)0);
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(-8, "fa_bwd: workspace must be 256-byte aligned");
   }
+  if (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2) return fail(-2, "fa_bwd: FP8 is forward-only (dtype %d)", dtype);
   if (int r = check_common("fa_bwd", B, H, N, D, dtype, softmax_scale)) return r;
   if (!q_strides || !k_strides || !v_strides || !do_strides || !dq_strides || !dk_strides || !dv_strides)
     return fail(-6, "fa_bwd: null stride array");

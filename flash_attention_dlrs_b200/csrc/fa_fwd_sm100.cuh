@@ -44,12 +44,20 @@ struct FwdParams {
   int q_blocks;              // ceil(N / 256)
 };
 
-template <int kD>
+// kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
+// (kind::f8f6f4; forward only — the reference's dtype map lists float8_e5m2, flash_attention_torch.py:15-16, and the
+// tutorial's fp8 path casts P to the FP8 type of V before P.V, flash_attention_openai_tutorial.py:66-67).
+template <int kD, int kElt = 1>
 struct FwdCfg {
-  static constexpr int kStages = (kD == 128) ? 2 : 4;
-  static constexpr int kTileBytes = 128 * kD * 2;  // one 128-row operand tile
-  static constexpr int kBoxBytes = 128 * 128;      // one 64-column box of it
-  static constexpr int kBoxes = kD / 64;
+  static constexpr bool kF8 = kElt >= 3;
+  static constexpr int kEltBytes = kF8 ? 1 : 2;
+  static constexpr int kRowBytes = kD * kEltBytes;         // one operand row
+  static constexpr int kStages = (kRowBytes == 256) ? 2 : 4;
+  static constexpr int kTileBytes = 128 * kRowBytes;       // one 128-row operand tile
+  static constexpr int kBoxBytes = 128 * 128;              // one 128-byte-wide box of it
+  static constexpr int kBoxes = kRowBytes / 128;
+  static constexpr int kBoxElems = 128 / kEltBytes;        // TMA x-coordinate step between boxes
+  static constexpr int kSteps = kRowBytes / 32;            // one MMA contracts 32 bytes of K
   static constexpr int kSmemQ = 2 * kTileBytes;
   static constexpr int kSmemKV = kStages * 2 * kTileBytes;
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*alignment slack*/;
@@ -57,11 +65,13 @@ struct FwdCfg {
   static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kD;
 };
 
-template <bool kBf16, int kD, bool kCausal>
+template <int kElt, int kD, bool kCausal>
 __global__ void __launch_bounds__(384, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
-  using Cfg = FwdCfg<kD>;
+  using Cfg = FwdCfg<kD, kElt>;
+  constexpr bool kF8 = Cfg::kF8, kBf16 = kElt == 1, kE5M2 = kElt == 4;
+  static_assert(!kF8 || kD == 128, "the FP8 forward runs at D = 128 (one 128-byte box per row); pad in the caller");
   constexpr int NS = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,7 +135,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int t = 0; t < ntiles; ++t) {
         mbar_arrive_expect_tx(&q_full[t], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
-          tma_load_4d(sQ + t * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmQ, &q_full[t], bx * 64, q0 + 128 * t, h,
+          tma_load_4d(sQ + t * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmQ, &q_full[t], bx * Cfg::kBoxElems, q0 + 128 * t, h,
                       b);
       }
       for (int j = 0; j < nkv_max; ++j) {
@@ -134,19 +144,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
-          tma_load_4d(sK + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &k_full[s], bx * 64, j * 128, h, b);
+          tma_load_4d(sK + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &k_full[s], bx * Cfg::kBoxElems, j * 128, h, b);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
-          tma_load_4d(sV + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &v_full[s], bx * 64, j * 128, h, b);
+          tma_load_4d(sV + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &v_full[s], bx * Cfg::kBoxElems, j * 128, h, b);
       }
     }
     __syncwarp();
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(kBf16, 128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_f16(kBf16, 128, kD, 0, 1);
+      constexpr uint32_t idesc_s = kF8 ? umma_idesc_f8(kE5M2, 128, 128, 0, 0) : umma_idesc_f16(kBf16, 128, 128, 0, 0);
+      constexpr uint32_t idesc_o = kF8 ? umma_idesc_f8(kE5M2, 128, kD, 0, 1) : umma_idesc_f16(kBf16, 128, kD, 0, 1);
       const uint32_t qlo = umma_lo_kmajor(smem_u32(sQ)), klo = umma_lo_kmajor(smem_u32(sK));
       const uint32_t vlo = umma_lo_mnmajor(smem_u32(sV), Cfg::kBoxBytes);
       constexpr uint32_t kTileLo = Cfg::kTileBytes >> 4;
@@ -158,10 +168,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_wait(&k_full[s], (j / NS) & 1);
         tc_fence_after();
         const uint32_t a0 = qlo + t * kTileLo, b0 = klo + s * kTileLo, d0 = tS(t);
-        static_for<0, kD / 16>([&](auto kc) {
+        static_for<0, Cfg::kSteps>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
-          umma_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
+          if constexpr (kF8)
+            umma8_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
+          else
+            umma_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
         });
         tc_commit(&s_full[t]);
         // last tile that reads K block j releases the stage
@@ -180,17 +193,25 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           mbar_wait(&v_full[s], (j / NS) & 1);
           // P arrives in two 64-key halves so the first half of P·V overlaps the second half of the exponentials
           const uint32_t dO_t = tO(t), aP = tS(t), bV = vlo + s * kTileLo;
+          // 16-bit P: 16 keys = 8 TMEM columns and 2048 bytes of V per MMA; FP8 P: 32 keys = 8 columns and 4096 bytes
+          constexpr int kPSteps = kF8 ? 4 : 8, kVStep = kF8 ? 2 : 1;
           mbar_wait(&p_full[t][0], j & 1);
           tc_fence_after();
-          static_for<0, 4>([&](auto kc) {
+          static_for<0, kPSteps / 2>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dO_t, aP, bV, idesc_o, (j > 0) || (k > 0));
+            if constexpr (kF8)
+              umma8_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, (j > 0) || (k > 0));
+            else
+              umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, (j > 0) || (k > 0));
           });
           mbar_wait(&p_full[t][1], j & 1);
           tc_fence_after();
-          static_for<4, 8>([&](auto kc) {
+          static_for<kPSteps / 2, kPSteps>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dO_t, aP, bV, idesc_o, 1u);
+            if constexpr (kF8)
+              umma8_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
+            else
+              umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
           });
           tc_commit(&o_full[t]);
           const bool last_user = (t == 1) || (nkv[1] <= j);
@@ -274,32 +295,66 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const float neg_ms = -m_used * sl2;
       const uint64_t sl2_2 = f32x2_pack(sl2, sl2), nm2 = f32x2_pack(neg_ms, neg_ms);
       uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};   // four packed partial row sums (8 fp32 chains)
+      if constexpr (!kF8) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 16; ++i) {
 #if FA_ABLATE == 2
-          pk[i] = sr[c * 32 + 2 * i] ^ sr[c * 32 + 2 * i + 1];
-          continue;
+            pk[i] = sr[c * 32 + 2 * i] ^ sr[c * 32 + 2 * i + 1];
+            continue;
 #endif
-          const uint64_t x2 = f32x2_fma(f32x2_pack_bits(sr[c * 32 + 2 * i], sr[c * 32 + 2 * i + 1]), sl2_2, nm2);
-          float x0, x1;
-          f32x2_unpack(x2, x0, x1);
-          float p0, p1;
-          if (((kD == 64 ? FA_FWD_POLY_MASK_D64 : FA_FWD_POLY_MASK_D128) >> (i & 7)) & 1) {   // FMA-pipe exp2
-            ex2_poly_x2(x0, x1, p0, p1);
-          } else {
-            p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const uint64_t x2 = f32x2_fma(f32x2_pack_bits(sr[c * 32 + 2 * i], sr[c * 32 + 2 * i + 1]), sl2_2, nm2);
+            float x0, x1;
+            f32x2_unpack(x2, x0, x1);
+            float p0, p1;
+            if (((kD == 64 ? FA_FWD_POLY_MASK_D64 : FA_FWD_POLY_MASK_D128) >> (i & 7)) & 1) {   // FMA-pipe exp2
+              ex2_poly_x2(x0, x1, p0, p1);
+            } else {
+              p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            }
+            ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));
+            pk[i] = pack2<kBf16>(p0, p1);
           }
-          ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));
-          pk[i] = pack2<kBf16>(p0, p1);
+          tmem_st_x16(tS + c * 16, pk);
+          if (c == 1) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[t][0]);
+          }
         }
-        tmem_st_x16(tS + c * 16, pk);
-        if (c == 1) {
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&p_full[t][0]);
+      } else {
+        // FP8 P: four keys per 32-bit TMEM column, 64 keys = 16 columns per store
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int e = c * 64 + 4 * i;
+            float x0, x1, x2, x3;
+            f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nm2), x0, x1);
+            f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e + 2], sr[e + 3]), sl2_2, nm2), x2, x3);
+            float p0, p1, p2, p3;
+            if ((FA_FWD_POLY_MASK_D128 >> ((2 * i) & 7)) & 1) {
+              ex2_poly_x2(x0, x1, p0, p1);
+            } else {
+              p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            }
+            if ((FA_FWD_POLY_MASK_D128 >> ((2 * i + 1) & 7)) & 1) {
+              ex2_poly_x2(x2, x3, p2, p3);
+            } else {
+              p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+            }
+            ls[i & 3] = f32x2_add(ls[i & 3], f32x2_add(f32x2_pack(p0, p1), f32x2_pack(p2, p3)));
+            pk[i] = pack4_f8<kE5M2>(p0, p1, p2, p3);
+          }
+          tmem_st_x16(tS + c * 16, pk);
+          if (c == 0) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[t][0]);
+          }
         }
       }
       float la, lb, lc, ld;
@@ -316,22 +371,36 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_after();
       const float inv_l = 1.0f / l;
       const bool in_range = q_row < p.N;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_sB + (int64_t)h * p.o_sH +
-                       (int64_t)q_row * p.o_sN;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                      ((int64_t)b * p.o_sB + (int64_t)h * p.o_sH + (int64_t)q_row * p.o_sN) * Cfg::kEltBytes;
 #pragma unroll
       for (int c = 0; c < kD / 32; ++c) {
         uint32_t orr[32];
         tmem_ld_x32(tO + c * 32, orr);
         tc_wait_ld();
         if (in_range) {
+          if constexpr (!kF8) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 v;
-            v.x = pack2<kBf16>(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
-            v.y = pack2<kBf16>(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
-            v.z = pack2<kBf16>(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
-            v.w = pack2<kBf16>(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = v;
+            for (int i = 0; i < 4; ++i) {
+              uint4 v;
+              v.x = pack2<kBf16>(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
+              v.y = pack2<kBf16>(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
+              v.z = pack2<kBf16>(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
+              v.w = pack2<kBf16>(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + (c * 32 + i * 8) * 2) = v;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint32_t w[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int e = 16 * i + 4 * u;
+                w[u] = pack4_f8<kE5M2>(__uint_as_float(orr[e]) * inv_l, __uint_as_float(orr[e + 1]) * inv_l,
+                                       __uint_as_float(orr[e + 2]) * inv_l, __uint_as_float(orr[e + 3]) * inv_l);
+              }
+              *reinterpret_cast<uint4*>(orow + c * 32 + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
         }
       }

@@ -329,6 +329,67 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int is_bf16, int M, int N,
   return umma_idesc_f16_ab(is_bf16, is_bf16, M, N, a_mn_major, b_mn_major);
 }
 
+// Instruction descriptor for kind::f8f6f4 with 8-bit floating-point inputs (fp32 accumulate): same fields as
+// kind::f16; A / B format 0 = E4M3, 1 = E5M2.  One instruction contracts 32 elements (32 bytes) of K.  MN-major
+// operands are legal for the 8-bit formats.
+__host__ __device__ constexpr uint32_t umma_idesc_f8(int is_e5m2, int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(is_e5m2) << 7) | (static_cast<uint32_t>(is_e5m2) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// FP8 issue-loop variants of umma_ss_off / umma_ts_off (compile-time offsets added to uniform base low words).
+template <uint32_t kOffA, uint32_t kOffB>
+__device__ __forceinline__ void umma8_ss_off(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 al, %1, %6;\n\t"
+      "add.u32 bl, %2, %7;\n\t"
+      "mov.b64 da, {al, %5};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA), "n"(kOffB)
+      : "memory");
+}
+template <uint32_t kOffA, uint32_t kOffB>
+__device__ __forceinline__ void umma8_ts_off(uint32_t tmem_d, uint32_t tmem_a_base, uint32_t b_base, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 ta, bl;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 ta, %1, %6;\n\t"
+      "add.u32 bl, %2, %7;\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [ta], db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA),
+        "n"(kOffB)
+      : "memory");
+}
+// four fp32 -> four packed FP8 values (RN, saturating to the largest finite value); `a` goes to bits [0,8).
+template <bool kE5M2>
+__device__ __forceinline__ uint32_t pack4_f8(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  if constexpr (kE5M2) {
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  } else {
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  }
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]     (single thread issues)
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                         uint32_t accumulate) {

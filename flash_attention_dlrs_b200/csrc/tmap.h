@@ -48,4 +48,22 @@ inline int make_tmap_bhnd_16bit(CUtensorMap* out, const void* base, int is_bf16,
   return r == CUDA_SUCCESS ? 0 : -(200 + (int)r);
 }
 
+// 8-bit element tensor (B, H, N, D) with element (= byte) strides {sB, sH, sN, 1}; box = 128 x box_rows (x1x1) bytes,
+// SWIZZLE_128B, out-of-bounds rows read as zero.  Used by the FP8 forward (D = 128: one box per 128-row tile).
+inline int make_tmap_bhnd_8bit(CUtensorMap* out, const void* base, int B, int H, int N, int D, int64_t sB, int64_t sH,
+                               int64_t sN, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -100;
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sN, (cuuint64_t)sH, (cuuint64_t)sB};
+  if (H == 1) strides[1] = strides[0] * (cuuint64_t)N;
+  if (B == 1) strides[2] = strides[1] * (cuuint64_t)H;
+  cuuint32_t box[4] = {128u, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(200 + (int)r);
+}
+
 }  // namespace fa

@@ -9,7 +9,8 @@ Differences from the reference, all deliberate:
   * the kernels are hand-written sm_100a CUDA reached through libfa_b200.so (no Triton, no autotune);
   * the backward is deterministic, so FlashAttentionDeterministic is the same Function;
   * L (base-2 logsumexp, flash_attention_kernels.py:106) is kept in float32 instead of the input dtype;
-  * bfloat16 is accepted, float64 / float8_e5m2 are not;
+  * bfloat16 is accepted; float8_e5m2 (in the reference's dtype map) and float8_e4m3fn run the forward only (P is cast
+    to the FP8 type before P.V, as the tutorial's fp8 path does, flash_attention_openai_tutorial.py:66-67); float64 is not;
   * head sizes that need padding also work in backward (the reference's padded backward is broken).
 """
 from __future__ import annotations

@@ -424,3 +424,118 @@ def test_backward_variants_bit_identical_many_heads(causal):
             again = _native.backward(Q, K, V, O, dO, L, causal, 0.09, which=which)
             for a, b in zip(first, again):
                 assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ streams and graphs
+def test_cuda_graph_capture_and_replay_bitwise():
+    """The C-ABI entry points never synchronise or allocate: forward + backward can be captured in a CUDA graph on a
+    side stream and replayed; replays reproduce the eager result bit for bit (also for the single-pass backward, whose
+    workspace counters are reset by a captured memset)."""
+    B, H, N, D = 1, 4, 512, 128
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(7, B, H, N, D, torch.bfloat16))
+    eager_O, eager_L = _native.forward(Q, K, V, True, 0.09)
+    eager_g = _native.backward(Q, K, V, eager_O, dO, eager_L, True, 0.09)
+    eager_f = _native.backward(Q, K, V, eager_O, dO, eager_L, True, 0.09, which=_native.BWD_FUSED)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):   # warm-up on the capture stream (function attributes, allocator pools)
+            o, l = _native.forward(Q, K, V, True, 0.09)
+            _native.backward(Q, K, V, o, dO, l, True, 0.09)
+            _native.backward(Q, K, V, o, dO, l, True, 0.09, which=_native.BWD_FUSED)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_O, g_L = _native.forward(Q, K, V, True, 0.09)
+        g_g = _native.backward(Q, K, V, g_O, dO, g_L, True, 0.09)
+        g_f = _native.backward(Q, K, V, g_O, dO, g_L, True, 0.09, which=_native.BWD_FUSED)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g_O, eager_O) and torch.equal(g_L, eager_L)
+    for a, b in zip(g_g + g_f, eager_g + eager_f):
+        assert torch.equal(a, b)
+
+
+def test_concurrent_streams_and_threads():
+    """Re-entrant and thread-safe: two host threads launch on their own streams at the same time."""
+    import threading
+    B, H, N, D = 1, 4, 1024, 64
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(9, B, H, N, D, torch.float16))
+    want_O, want_L = _native.forward(Q, K, V, False, 0.125)
+    want_g = _native.backward(Q, K, V, want_O, dO, want_L, False, 0.125)
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def worker(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(5):
+                    o, l = _native.forward(Q, K, V, False, 0.125)
+                    g = _native.backward(Q, K, V, o, dO, l, False, 0.125)
+            st.synchronize()
+            results[i] = (o, l, g)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for o, l, g in results.values():
+        assert torch.equal(o, want_O) and torch.equal(l, want_L)
+        for a, b in zip(g, want_g):
+            assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ FP8 forward
+FP8_FORMATS = {torch.float8_e4m3fn: (3, -6), torch.float8_e5m2: (2, -14)}   # mantissa bits, smallest normal exponent
+
+
+def fp8_o_bound(Qf, Kf, Vf, scale, causal, dtype):
+    """Entry-wise bound of what the SPECIFIED FP8 arithmetic may differ from the fp64 ground truth by: 2e-3, plus the
+    output's own rounding (half an ulp of the FP8 output, flash_attention_torch.py:50 allocates O in the input dtype),
+    plus P rounded to FP8 before P.V (flash_attention_openai_tutorial.py:66-67: relative half-ulp 2^-(m+1), first order
+    2^-(m+1) sum_j P_ij |V_jd|), plus the P entries below the smallest FP8 subnormal, which flush to zero."""
+    m, emin = FP8_FORMATS[dtype]
+    S = orc._scores_fp64(Qf, Kf, scale, causal)
+    E = torch.exp(S - S.amax(-1, keepdim=True))
+    P = E / E.sum(-1, keepdim=True)
+    absV = Vf.double().abs()
+    O = P @ Vf.double()
+    half_ulp = torch.exp2(torch.floor(torch.log2(O.abs().clamp_min(2.0 ** emin))) - m - 1)
+    p_round = 2.0 ** -(m + 1) * (P @ absV)
+    flush = (P * (E < 2.0 ** (emin - m + 1))) @ absV
+    return O, 2e-3 + half_ulp + p_round + flush
+
+
+@pytest.mark.parametrize("dtype", list(FP8_FORMATS))
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("N,d", [(128, 128), (384, 128), (1000, 128), (512, 64), (300, 80)])
+def test_fp8_forward_parity(dtype, causal, N, d):
+    B, H = 2, 3
+    scale = 1.0 / math.sqrt(d)
+    g = torch.Generator().manual_seed(21)
+    Q, K, V = (torch.randn(B, H, N, d, generator=g).to(dtype) for _ in range(3))
+    O, L = flash_attention_forward(Q.to(DEV), K.to(DEV), V.to(DEV), DEV, causal, scale)
+    torch.cuda.synchronize()
+    assert O.dtype == dtype and O.shape == (B, H, N, d) and L.dtype == torch.float32
+    ref_O, bound = fp8_o_bound(Q.float(), K.float(), V.float(), scale, causal, dtype)
+    err = (O.cpu().double() - ref_O).abs()
+    assert (err <= bound).all(), f"O err {err.max().item():.3e} (worst excess {(err - bound).max().item():.3e})"
+    ref = orc.attention_fp64(Q.float(), K.float(), V.float(), scale, causal)
+    assert (L.cpu().double() - ref[1]).abs().max().item() <= 2e-3
+
+
+def test_fp8_is_forward_only_and_deterministic():
+    Q, K, V = (torch.randn(1, 2, 256, 128, generator=torch.Generator().manual_seed(s)).to(torch.float8_e5m2).to(DEV)
+               for s in (1, 2, 3))
+    O1, L1 = flash_attention_forward(Q, K, V, DEV, True, 0.1)
+    O2, L2 = flash_attention_forward(Q, K, V, DEV, True, 0.1)
+    assert torch.equal(O1.view(torch.uint8), O2.view(torch.uint8)) and torch.equal(L1, L2)
+    with pytest.raises(TypeError):
+        flash_attention_backward(Q, K, V, O1, O1, L1, DEV, False, True, 0.1)

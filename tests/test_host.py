@@ -68,6 +68,9 @@ def test_dtype_whitelist():
     assert fat.convert_triton_dtype(torch.float16) == _lib.FA_DTYPE_F16
     assert fat.convert_triton_dtype(torch.bfloat16) == _lib.FA_DTYPE_BF16
     assert fat.convert_triton_dtype(torch.float32) == _lib.FA_DTYPE_F32
+    # FP8 (forward only): float8_e5m2 is in the reference's own map (flash_attention_torch.py:15-16)
+    assert fat.convert_triton_dtype(torch.float8_e5m2) == _lib.FA_DTYPE_F8E5M2 == 4
+    assert fat.convert_triton_dtype(torch.float8_e4m3fn) == _lib.FA_DTYPE_F8E4M3 == 3
     with pytest.raises(TypeError, match="not supported"):
         fat.convert_triton_dtype(torch.float64)
     with pytest.raises(TypeError):
@@ -87,8 +90,16 @@ def test_padded_head_dim():
     assert _native.padded_head_dim(8, torch.float32) == 16
     assert _native.padded_head_dim(40, torch.float32) == 64
     assert _native.padded_head_dim(128, torch.float32) == 128
+    assert _native.padded_head_dim(64, torch.float8_e5m2) == 128
     with pytest.raises(ValueError):
         _native.padded_head_dim(129, torch.float32)
+
+
+def test_fp8_padding_is_bytewise_zero():
+    t = torch.randn(1, 2, 5, 40).to(torch.float8_e4m3fn)
+    p = _native._pad_d(t, 128)
+    assert p.dtype == t.dtype and p.shape == (1, 2, 5, 128)
+    assert torch.equal(p.view(torch.uint8)[..., :40], t.view(torch.uint8)) and not p.view(torch.uint8)[..., 40:].any()
 
 
 def test_kernel_ready_views():
