@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "fa_version",
     "fa_last_error",
     "fa_fwd",
+    "fa_fwd_peers",
     "fa_bwd_preprocess",
     "fa_bwd_workspace_bytes",
     "fa_bwd",
@@ -91,6 +92,8 @@ def _declare(lib):
     lib.fa_last_error.argtypes = []
     lib.fa_fwd.restype = i
     lib.fa_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, vp]
+    lib.fa_fwd_peers.restype = i
+    lib.fa_fwd_peers.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, i, ctypes.POINTER(vp), vp]
     lib.fa_bwd_preprocess.restype = i
     lib.fa_bwd_preprocess.argtypes = [vp, vp, vp, i, i, i, i, st, st, i, vp]
     lib.fa_bwd_workspace_bytes.restype = sz

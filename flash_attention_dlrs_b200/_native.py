@@ -68,20 +68,37 @@ def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
 
-def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float):
-    """O (B,H,N,d) in the input dtype and L (B,H,N) float32 in log2 units.  Inputs already validated."""
+def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float, out=None,
+            peer_ptrs=()):
+    """O (B,H,N,d) in the input dtype and L (B,H,N) float32 in log2 units.  Inputs already validated.
+
+    `out` = (data_ptr, element strides (sB, sH, sN, 1)) makes the kernel write O at a caller-owned address (a window of
+    a gathered buffer, possibly an NVLS multicast address) instead of a fresh tensor, and `peer_ptrs` (<= 7 device
+    pointers) adds peer-mapped copies with the same strides (fa_fwd_peers); both need an unpadded head size and return
+    O = None."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
     d_run = padded_head_dim(d, Q.dtype)
     q, k, v = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V))
-    O = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
     L = torch.empty((B, H, N), dtype=torch.float32, device=Q.device)
+    if out is None:
+        O = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
+        o_ptr, o_strides = _ptr(O), _lib.strides4(O)
+    else:
+        if d_run != d:
+            raise ValueError(f"writing O in place needs a head size the kernels run at (d={d} is padded to {d_run})")
+        O = None
+        o_ptr, o_strides = ctypes.c_void_p(int(out[0])), _lib._I64x4(*out[1])
+    peers = (ctypes.c_void_p * max(len(peer_ptrs), 1))(*[int(x) for x in peer_ptrs])
     with torch.cuda.device(Q.device):
-        rc = lib.fa_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(O), _ptr(L), B, H, N, d_run,
-                        _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(O),
-                        code, float(softmax_scale), int(bool(causal)), _stream_ptr(Q.device))
+        rc = lib.fa_fwd_peers(_ptr(q), _ptr(k), _ptr(v), o_ptr, _ptr(L), B, H, N, d_run,
+                              _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), o_strides,
+                              code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers,
+                              _stream_ptr(Q.device))
     _lib.check(rc, "fa_fwd")
+    if O is None:
+        return None, L
     return (O if d_run == d else O[..., :d]), L
 
 

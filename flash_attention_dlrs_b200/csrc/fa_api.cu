@@ -200,7 +200,19 @@ const char* fa_last_error(void) { return g_err; }
 int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
+  return fa_fwd_peers(q, k, v, o, lse, B, H, N, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale,
+                      causal, 0, nullptr, stream);
+}
+
+int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
+                 const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+                 const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
+                 void* const* peer_o, void* stream) {
   g_err[0] = 0;
+  if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_o)) return fail(-12, "fa_fwd_peers: 0 <= n_peers <= 7 and peer_o non-null");
+  if (n_peers > 0 && dtype == FA_DTYPE_F32) return fail(-12, "fa_fwd_peers: peer copies are implemented for the 16-bit and FP8 kernels");
+  for (int i = 0; i < n_peers; ++i)
+    if (!peer_o[i] || (reinterpret_cast<uintptr_t>(peer_o[i]) & 15u)) return fail(-8, "fa_fwd_peers: peer_o[%d] must be a 16-byte aligned device pointer", i);
   if (int r = check_common("fa_fwd", B, H, N, D, dtype, softmax_scale)) return r;
   if (!q_strides || !k_strides || !v_strides || !o_strides) return fail(-6, "fa_fwd: null stride array");
   if (int r = check_tensor("fa_fwd", "q", q, q_strides, dtype, B, H)) return r;
@@ -240,6 +252,8 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
   p.o_sB = o_strides[0], p.o_sH = o_strides[1], p.o_sN = o_strides[2];
   p.scale_log2 = softmax_scale * kLog2e;
   p.q_blocks = (N + 255) / 256;
+  p.n_peer = n_peers;
+  for (int i = 0; i < n_peers; ++i) p.o_peer[i] = peer_o[i];
 #define FA_FWD_CASE(E, DD, C) \
   if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
   FA_FWD_CASE(FA_DTYPE_BF16, 128, true)

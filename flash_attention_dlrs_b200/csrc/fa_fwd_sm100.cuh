@@ -32,6 +32,9 @@
 #ifndef FA_FWD_POLY_MASK_D64
 #define FA_FWD_POLY_MASK_D64 0x92
 #endif
+#ifndef FA_FWD_POLY_MASK_F8
+#define FA_FWD_POLY_MASK_F8 0x92
+#endif
 
 namespace fa {
 
@@ -42,6 +45,12 @@ struct FwdParams {
   int64_t o_sB, o_sH, o_sN;  // element strides of O (last dim contiguous)
   float scale_log2;          // softmax_scale * log2(e)
   int q_blocks;              // ceil(N / 256)
+  // Fused all-gather epilogue (head-sharded multi-GPU): every O row is also stored, with the same strides, into the
+  // peer-mapped windows of the other GPUs' gathered output (NVLink P2P stores issued by the epilogue warps, so the
+  // transfer overlaps the remaining tiles).  With NVLS the caller passes a multicast address as `o` instead and the
+  // switch replicates each store; n_peer is then 0.
+  void* o_peer[7];
+  int n_peer;
 };
 
 // kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
@@ -336,12 +345,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nm2), x0, x1);
             f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e + 2], sr[e + 3]), sl2_2, nm2), x2, x3);
             float p0, p1, p2, p3;
-            if ((FA_FWD_POLY_MASK_D128 >> ((2 * i) & 7)) & 1) {
+            if ((FA_FWD_POLY_MASK_F8 >> ((2 * i) & 7)) & 1) {
               ex2_poly_x2(x0, x1, p0, p1);
             } else {
               p0 = ex2_approx(x0), p1 = ex2_approx(x1);
             }
-            if ((FA_FWD_POLY_MASK_D128 >> ((2 * i + 1) & 7)) & 1) {
+            if ((FA_FWD_POLY_MASK_F8 >> ((2 * i + 1) & 7)) & 1) {
               ex2_poly_x2(x2, x3, p2, p3);
             } else {
               p2 = ex2_approx(x2), p3 = ex2_approx(x3);
@@ -371,36 +380,66 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_after();
       const float inv_l = 1.0f / l;
       const bool in_range = q_row < p.N;
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
-                      ((int64_t)b * p.o_sB + (int64_t)h * p.o_sH + (int64_t)q_row * p.o_sN) * Cfg::kEltBytes;
+      // Epilogue: O_t / l -> output dtype -> this tile's Q staging buffer (dead since its last S MMA; same size as the O
+      // tile) -> global.  Going through shared memory turns "thread = row" into "warp = two full rows": every warp
+      // store covers 512 contiguous bytes, which is what makes the peer / multicast copies of the fused all-gather
+      // travel as full NVLink packets instead of one packet per 16 bytes.
+      constexpr int kRowChunks = Cfg::kRowBytes / 16;
+      const uint32_t stage = smem_u32(sQ + t * Cfg::kTileBytes);
 #pragma unroll
       for (int c = 0; c < kD / 32; ++c) {
         uint32_t orr[32];
         tmem_ld_x32(tO + c * 32, orr);
         tc_wait_ld();
-        if (in_range) {
-          if constexpr (!kF8) {
+        if constexpr (!kF8) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 v;
-              v.x = pack2<kBf16>(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
-              v.y = pack2<kBf16>(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
-              v.z = pack2<kBf16>(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
-              v.w = pack2<kBf16>(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + (c * 32 + i * 8) * 2) = v;
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = pack2<kBf16>(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
+            const uint32_t bq = pack2<kBf16>(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
+            const uint32_t cq = pack2<kBf16>(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
+            const uint32_t dq = pack2<kBf16>(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
+            const uint32_t ch = c * 4 + i;   // 16-byte chunk of the row
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage + row * Cfg::kRowBytes +
+                                                                            ((ch ^ (row & 7)) << 4)),
+                         "r"(a), "r"(bq), "r"(cq), "r"(dq)
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = 16 * i + 4 * u;
+              w[u] = pack4_f8<kE5M2>(__uint_as_float(orr[e]) * inv_l, __uint_as_float(orr[e + 1]) * inv_l,
+                                     __uint_as_float(orr[e + 2]) * inv_l, __uint_as_float(orr[e + 3]) * inv_l);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint32_t w[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int e = 16 * i + 4 * u;
-                w[u] = pack4_f8<kE5M2>(__uint_as_float(orr[e]) * inv_l, __uint_as_float(orr[e + 1]) * inv_l,
-                                       __uint_as_float(orr[e + 2]) * inv_l, __uint_as_float(orr[e + 3]) * inv_l);
-              }
-              *reinterpret_cast<uint4*>(orow + c * 32 + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            const uint32_t ch = c * 2 + i;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage + row * Cfg::kRowBytes +
+                                                                            ((ch ^ (row & 7)) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
+        }
+      }
+      named_bar_sync(2 + t, 128);   // the 128 threads of this tile
+      {
+        const int tid = threadIdx.x & 127;
+        const int64_t tile_off = ((int64_t)b * p.o_sB + (int64_t)h * p.o_sH) * Cfg::kEltBytes;
+        const int64_t row_pitch = p.o_sN * Cfg::kEltBytes;
+        const int row0 = q0 + 128 * t;
+#pragma unroll 4
+        for (int it = 0; it < kRowChunks; ++it) {
+          const int idx = it * 128 + tid;
+          const int r = idx / kRowChunks, ch = idx - r * kRowChunks;
+          if (row0 + r < p.N) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stage + r * Cfg::kRowBytes + ((ch ^ (r & 7)) << 4)));
+            const int64_t off = tile_off + (int64_t)(row0 + r) * row_pitch + ch * 16;
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.o) + off) = v;
+            for (int g = 0; g < p.n_peer; ++g) *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.o_peer[g]) + off) = v;
           }
         }
       }

@@ -41,13 +41,60 @@ def all_gather_heads(local: torch.Tensor, H: int, group=None) -> torch.Tensor:
     return out
 
 
+class PeerGatherBuffer:
+    """Gathered output (B, H, N, d) that every rank's forward kernel writes DIRECTLY: rank g's epilogue stores its head
+    slice into all ranks' copies over NVLink while it is still computing the remaining tiles — through one NVLS
+    multicast store per 16 bytes when the switch supports it, otherwise through per-peer P2P stores (fa_fwd_peers).
+    Replaces the NCCL all-gather that would follow the kernel.  Built on torch's symmetric memory (allocation,
+    handle exchange and barrier are plumbing; the data path is the attention kernel itself)."""
+
+    def __init__(self, B: int, H: int, N: int, d: int, dtype: torch.dtype, device, group=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("peer gather is a single-box path (<= 8 GPUs)")
+        self.tensor = symm_mem.empty((B, H, N, d), dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        self.peer_base = [int(p) for p in self.handle.buffer_ptrs]
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.multicast_base = mc if (use_multicast and mc) else 0
+        self.H = H
+
+    def window(self, rank: int):
+        """(local view, [(data_ptr, strides)] for the kernel) of rank `rank`'s head slice."""
+        h0, h1 = head_range(self.H, rank, self.world)
+        return self.tensor[:, h0:h1]
+
+    def forward_into(self, Q_local, K_local, V_local, causal, softmax_scale):
+        """Run this rank's forward with the fused gather; returns (gathered tensor, L_local).  The gathered tensor is
+        complete on every rank after the barrier this method issues on the current stream."""
+        from . import _native
+
+        view = self.window(self.rank)
+        assert view.shape == Q_local.shape, (view.shape, Q_local.shape)
+        off = view.data_ptr() - self.tensor.data_ptr()
+        strides = tuple(view.stride())
+        if self.multicast_base:
+            _, L = _native.forward(Q_local, K_local, V_local, causal, softmax_scale,
+                                   out=(self.multicast_base + off, strides))
+        else:
+            peers = [b + off for r, b in enumerate(self.peer_base) if r != self.rank]
+            _, L = _native.forward(Q_local, K_local, V_local, causal, softmax_scale,
+                                   out=(view.data_ptr(), strides), peer_ptrs=peers)
+        self.handle.barrier()
+        return self.tensor, L
+
+
 def head_sharded_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0, group=None,
                            gather: bool = False, attn_fn=None):
     """Attention over this rank's head slice of replicated (B, H, N, d) inputs.
 
     Returns the local (B, h_local, N, d) output, or the full (B, H, N, d) output on every rank when
-    `gather=True`.  The head slice is a strided view (no copy); `attn_fn(q, k, v, causal, softmax_scale)`
-    defaults to FlashAttention.apply.
+    `gather=True` (NCCL all-gather after the kernel) or `gather=<PeerGatherBuffer>` (the kernel's epilogue writes every
+    rank's copy itself, no collective).  The head slice is a strided view (no copy);
+    `attn_fn(q, k, v, causal, softmax_scale)` defaults to FlashAttention.apply.
     """
     if attn_fn is None:
         from .flash_attention_torch import FlashAttention
@@ -56,6 +103,8 @@ def head_sharded_attention(Q, K, V, causal: bool = False, softmax_scale: float =
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     H = Q.shape[1]
     h0, h1 = head_range(H, rank, world)
+    if isinstance(gather, PeerGatherBuffer):
+        return gather.forward_into(Q[:, h0:h1], K[:, h0:h1], V[:, h0:h1], causal, softmax_scale)[0]
     o_local = attn_fn(Q[:, h0:h1], K[:, h0:h1], V[:, h0:h1], causal, softmax_scale)
     if not gather or world == 1:
         return o_local

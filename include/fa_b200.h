@@ -46,6 +46,17 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream);
 
+/* fa_fwd with a fused all-gather epilogue for head-sharded multi-GPU runs (16-bit and FP8 dtypes): every row of O is
+ * stored to `o` AND, with the same strides, to the `n_peers` (<= 7) peer-mapped windows `peer_o[i]` of the other GPUs'
+ * gathered output buffers — NVLink peer-to-peer stores issued by the epilogue warps, overlapped with the remaining tiles.
+ * With NVLS, pass a multicast address as `o` and n_peers = 0: the switch replicates each store.  The caller synchronises
+ * the ranks (e.g. a barrier on the stream) before anybody reads the gathered buffer.  The reference has no multi-GPU path;
+ * this stands where a caller would otherwise follow fa_fwd by an NCCL all-gather of O along H. */
+int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
+                 const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+                 const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
+                 void* const* peer_o, void* stream);
+
 /* Backward preprocess: delta[b,h,i] = sum_d O[b,h,i,d] * dO[b,h,i,d]  (fp32 accumulate).
  * Replaces bwd_D_kernel[grid](...) at flash_attention_torch.py:125-133 and flash_attention_wrappers.py:110-118. */
 int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int H, int N, int D,

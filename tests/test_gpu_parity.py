@@ -539,3 +539,25 @@ def test_fp8_is_forward_only_and_deterministic():
     assert torch.equal(O1.view(torch.uint8), O2.view(torch.uint8)) and torch.equal(L1, L2)
     with pytest.raises(TypeError):
         flash_attention_backward(Q, K, V, O1, O1, L1, DEV, False, True, 0.1)
+
+
+# ------------------------------------------------------------------------------------------------ fused gather epilogue
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float8_e4m3fn])
+def test_forward_writes_in_place_and_to_peer_windows(dtype):
+    """fa_fwd_peers on one GPU: O goes to a strided window of a caller-owned 'gathered' buffer and to two more windows
+    standing in for peer GPUs; all copies equal the plain forward bit for bit, L too."""
+    B, H, N, D, Htot, h0 = 2, 3, 384, 128, 8, 2
+    g = torch.Generator().manual_seed(5)
+    Q, K, V = (torch.randn(B, H, N, D, generator=g).to(dtype).to(DEV) for _ in range(3))
+    want_O, want_L = _native.forward(Q, K, V, True, 0.09)
+    bufs = [torch.zeros(B, Htot, N, D, dtype=torch.uint8 if dtype.itemsize == 1 else dtype, device=DEV).view(dtype)
+            for _ in range(3)]
+    views = [b[:, h0:h0 + H] for b in bufs]
+    none, L = _native.forward(Q, K, V, True, 0.09, out=(views[0].data_ptr(), tuple(views[0].stride())),
+                              peer_ptrs=[v.data_ptr() for v in views[1:]])
+    torch.cuda.synchronize()
+    assert none is None and torch.equal(L, want_L)
+    raw = lambda t: t.contiguous().view(torch.uint8)
+    for b, v in zip(bufs, views):
+        assert torch.equal(raw(v), raw(want_O))
+        assert not raw(b[:, :h0]).any() and not raw(b[:, h0 + H:]).any()   # nothing outside the window
