@@ -561,3 +561,24 @@ def test_forward_writes_in_place_and_to_peer_windows(dtype):
     for b, v in zip(bufs, views):
         assert torch.equal(raw(v), raw(want_O))
         assert not raw(b[:, :h0]).any() and not raw(b[:, h0 + H:]).any()   # nothing outside the window
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own script
+def test_reference_gradcheck_script_runs_unmodified(capsys):
+    """src/test_torch.py of the reference, byte for byte (baseline/_ref/src, an untouched copy), with only sys.path
+    pointing `flash_attention_torch` at flash_attention_dlrs_b200/compat: both gradchecks must report success."""
+    import runpy
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "baseline", "_ref", "src", "test_torch.py")
+    if not os.path.exists(script):
+        pytest.skip("baseline/_ref/src not present (tools/fetch_reference.sh)")
+    compat = os.path.join(root, "flash_attention_dlrs_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        sys.path.remove(compat)
+    out = capsys.readouterr().out
+    assert "Non-deterministic backwards test successful" in out, out
+    assert "Deterministic backwards test successful" in out, out
