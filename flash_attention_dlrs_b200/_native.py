@@ -40,6 +40,8 @@ def padded_head_dim(d: int, dtype: torch.dtype) -> int:
 
 def _kernel_ready(t: torch.Tensor) -> torch.Tensor:
     """A view the kernels can address: unit inner stride, 16-byte aligned base and outer strides."""
+    if t.is_contiguous() and t.data_ptr() % 16 == 0 and (t.shape[-1] * t.element_size()) % 16 == 0:
+        return t   # the common case, without the stride arithmetic (this function is on the launch path)
     gran = 16 // t.element_size()
     B, H, N, _ = t.shape
     sB, sH, sN, sD = t.stride()
@@ -61,7 +63,27 @@ def _pad_d(t: torch.Tensor, d_run: int) -> torch.Tensor:
 
 
 def _stream_ptr(dev: torch.device) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    """torch's current stream on `dev` as a cudaStream_t (the raw getter: this is on the launch path of every call)."""
+    idx = dev.index if dev.index is not None else torch._C._cuda_getDevice()
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` that costs nothing when `dev` is already current (the usual case)."""
+
+    __slots__ = ("guard",)
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index
+        self.guard = None if idx is None or idx == torch._C._cuda_getDevice() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
 
 
 def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
@@ -91,7 +113,7 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
         O = None
         o_ptr, o_strides = ctypes.c_void_p(int(out[0])), _lib._I64x4(*out[1])
     peers = (ctypes.c_void_p * max(len(peer_ptrs), 1))(*[int(x) for x in peer_ptrs])
-    with torch.cuda.device(Q.device):
+    with _on_device(Q.device):
         rc = lib.fa_fwd_peers(_ptr(q), _ptr(k), _ptr(v), o_ptr, _ptr(L), B, H, N, d_run,
                               _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), o_strides,
                               code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers,
@@ -109,7 +131,7 @@ def backward_preprocess(O: torch.Tensor, dO: torch.Tensor) -> torch.Tensor:
     code = dtype_code(O.dtype)
     o, do = _kernel_ready(O), _kernel_ready(dO)
     delta = torch.empty((B, H, N), dtype=torch.float32, device=O.device)
-    with torch.cuda.device(O.device):
+    with _on_device(O.device):
         rc = lib.fa_bwd_preprocess(_ptr(o), _ptr(do), _ptr(delta), B, H, N, d,
                                    _lib.strides4(o), _lib.strides4(do), code, _stream_ptr(O.device))
     _lib.check(rc, "fa_bwd_preprocess")
@@ -131,19 +153,17 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
         raise TypeError(f"dtype {Q.dtype} not supported in backward (the FP8 path is forward-only).")
     d_run = padded_head_dim(d, Q.dtype)
     q, k, v, o, do = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V, O, dO))
-    lse = L.reshape(B, H, N).to(torch.float32).contiguous()
+    lse = L if (L.dtype == torch.float32 and L.is_contiguous()) else L.to(torch.float32).contiguous()  # (B,H,N[,1])
     if delta is None:
         delta = backward_preprocess(o, do)
-    dQ = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
-    dK = torch.empty_like(dQ)
-    dV = torch.empty_like(dQ)
+    dQ, dK, dV = torch.empty((3, B, H, N, d_run), dtype=Q.dtype, device=Q.device).unbind(0)   # one allocation
     if which is None:
         which = BWD_DKDV | BWD_DQ
     ws_bytes = lib.fa_bwd_workspace_bytes(B, H, N, d_run, code, int(bool(causal)), int(which))
     # scratch of the ordered dQ reduction, owned by the caching allocator like every other buffer (the reference
     # allocates its dQ lock buffers the same way, flash_attention_torch.py:107-109)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=Q.device) if ws_bytes else None
-    with torch.cuda.device(Q.device):
+    with _on_device(Q.device):
         rc = lib.fa_bwd_partial(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(lse), _ptr(delta), _ptr(dQ), _ptr(dK),
                                 _ptr(dV), _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, B, H, N,
                                 d_run, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),

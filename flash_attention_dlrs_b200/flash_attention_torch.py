@@ -45,7 +45,7 @@ class FlashAttention(torch.autograd.Function):
         _validate(Q, K, V)
         causal = bool(causal)
         softmax_scale = float(softmax_scale)
-        O, L = _native.forward(Q.detach(), K.detach(), V.detach(), causal, softmax_scale)
+        O, L = _native.forward(Q, K, V, causal, softmax_scale)   # Function.forward runs without graph recording
         # same saved set as the reference (flash_attention_torch.py:77), unpadded
         ctx.save_for_backward(Q, K, V, O, L)
         ctx.causal = causal
