@@ -584,16 +584,13 @@ def test_reference_gradcheck_script_runs_unmodified(capsys):
     assert "Deterministic backwards test successful" in out, out
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box")
-def test_fused_gather_epilogue_matches_nccl_all_gather_two_gpus():
-    """Two ranks (torchrun, NCCL for the rendezvous and the comparison path): the gathered O written by the forward
-    kernels' epilogues (NVLS multicast and / or P2P stores) equals forward + NCCL all-gather bit for bit."""
+def _run_peer_gather(nproc, port):
     import json
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29917", os.path.join(root, "tools", "multi_gpu_peer_gather.py"),
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tools", "multi_gpu_peer_gather.py"),
            "1", "8", "2048", "128"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -601,3 +598,17 @@ def test_fused_gather_epilogue_matches_nccl_all_gather_two_gpus():
     res = json.loads(lines[-1])
     flags = {k: v for k, v in res.items() if k.endswith("_equals_nccl_bitwise")}
     assert flags and all(flags.values()), res
+    return res
+
+
+def test_fused_gather_epilogue_single_rank():
+    """PeerGatherBuffer end to end with one rank (torchrun, symmetric-memory rendezvous, kernel writing O in place at
+    the buffer's address, barrier): equals the plain forward bit for bit."""
+    _run_peer_gather(1, 29916)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box")
+def test_fused_gather_epilogue_matches_nccl_all_gather_two_gpus():
+    """Two ranks (torchrun, NCCL for the rendezvous and the comparison path): the gathered O written by the forward
+    kernels' epilogues (NVLS multicast and / or P2P stores) equals forward + NCCL all-gather bit for bit."""
+    _run_peer_gather(2, 29917)
