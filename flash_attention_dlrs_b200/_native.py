@@ -90,22 +90,38 @@ def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _seqlens_arg(seqlens, B: int, device):
+    """(tensor kept alive, c_void_p) for the optional per-batch valid lengths: int32, contiguous, on `device`."""
+    if seqlens is None:
+        return None, ctypes.c_void_p(0)
+    t = torch.as_tensor(seqlens, device=device).to(torch.int32).contiguous()
+    if t.dim() != 1 or t.shape[0] != B:
+        raise ValueError(f"seqlens must have shape (B,) = ({B},), got {tuple(t.shape)}")
+    return t, _ptr(t)
+
+
 def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float, out=None,
-            peer_ptrs=()):
+            peer_ptrs=(), seqlens=None):
     """O (B,H,N,d) in the input dtype and L (B,H,N) float32 in log2 units.  Inputs already validated.
 
     `out` = (data_ptr, element strides (sB, sH, sN, 1)) makes the kernel write O at a caller-owned address (a window of
     a gathered buffer, possibly an NVLS multicast address) instead of a fresh tensor, and `peer_ptrs` (<= 7 device
     pointers) adds peer-mapped copies with the same strides (fa_fwd_peers); both need an unpadded head size and return
-    O = None."""
+    O = None.
+
+    `seqlens` (B,) int: key-padding mask — batch element b has seqlens[b] valid tokens; keys beyond are masked out and
+    the rows of O / L beyond are zero."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
     d_run = padded_head_dim(d, Q.dtype)
     q, k, v = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V))
-    L = torch.empty((B, H, N), dtype=torch.float32, device=Q.device)
+    sl, sl_ptr = _seqlens_arg(seqlens, B, Q.device)
+    new = torch.empty if sl is None else torch.zeros   # padded rows are not written by the kernels
+    L = new((B, H, N), dtype=torch.float32, device=Q.device)
     if out is None:
-        O = torch.empty((B, H, N, d_run), dtype=Q.dtype, device=Q.device)
+        O = (new((B, H, N, d_run), dtype=Q.dtype, device=Q.device) if Q.dtype not in FP8_DTYPES or sl is None
+             else torch.zeros((B, H, N, d_run), dtype=torch.uint8, device=Q.device).view(Q.dtype))
         o_ptr, o_strides = _ptr(O), _lib.strides4(O)
     else:
         if d_run != d:
@@ -116,7 +132,7 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
     with _on_device(Q.device):
         rc = lib.fa_fwd_peers(_ptr(q), _ptr(k), _ptr(v), o_ptr, _ptr(L), B, H, N, d_run,
                               _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), o_strides,
-                              code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers,
+                              code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers, sl_ptr,
                               _stream_ptr(Q.device))
     _lib.check(rc, "fa_fwd")
     if O is None:
@@ -141,11 +157,13 @@ def backward_preprocess(O: torch.Tensor, dO: torch.Tensor) -> torch.Tensor:
 BWD_DKDV, BWD_DQ, BWD_FUSED = 1, 2, 4
 
 
-def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int | None = None, delta=None):
+def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int | None = None, delta=None,
+             seqlens=None):
     """dQ, dK, dV (B,H,N,d) in the input dtype; deterministic (bit-identical across runs).
     `which` = None runs what fa_bwd runs: the two-kernel path (BWD_DKDV | BWD_DQ; either half can be selected alone,
     unselected outputs are uninitialised).  BWD_FUSED selects the single-pass kernel with the ordered dQ reduction
-    (16-bit inputs only).  `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch."""
+    (16-bit inputs only).  `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch.
+    `seqlens` as in forward(): gradient rows beyond seqlens[b] are zero (two-kernel path only)."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
@@ -156,7 +174,9 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
     lse = L if (L.dtype == torch.float32 and L.is_contiguous()) else L.to(torch.float32).contiguous()  # (B,H,N[,1])
     if delta is None:
         delta = backward_preprocess(o, do)
-    dQ, dK, dV = torch.empty((3, B, H, N, d_run), dtype=Q.dtype, device=Q.device).unbind(0)   # one allocation
+    sl, sl_ptr = _seqlens_arg(seqlens, B, Q.device)
+    new = torch.empty if sl is None else torch.zeros   # padded rows are not written by the kernels
+    dQ, dK, dV = new((3, B, H, N, d_run), dtype=Q.dtype, device=Q.device).unbind(0)   # one allocation
     if which is None:
         which = BWD_DKDV | BWD_DQ
     ws_bytes = lib.fa_bwd_workspace_bytes(B, H, N, d_run, code, int(bool(causal)), int(which))
@@ -168,7 +188,8 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
                                 _ptr(dV), _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, B, H, N,
                                 d_run, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),
                                 _lib.strides4(dQ), _lib.strides4(dK), _lib.strides4(dV),
-                                code, float(softmax_scale), int(bool(causal)), int(which), _stream_ptr(Q.device))
+                                code, float(softmax_scale), int(bool(causal)), int(which), sl_ptr,
+                                _stream_ptr(Q.device))
     _lib.check(rc, "fa_bwd")
     if d_run != d:
         dQ, dK, dV = dQ[..., :d], dK[..., :d], dV[..., :d]

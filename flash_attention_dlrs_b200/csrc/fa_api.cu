@@ -193,7 +193,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 2; }
+int fa_version(void) { return 3; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -201,13 +201,13 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
   return fa_fwd_peers(q, k, v, o, lse, B, H, N, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale,
-                      causal, 0, nullptr, stream);
+                      causal, 0, nullptr, nullptr, stream);
 }
 
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
-                 void* const* peer_o, void* stream) {
+                 void* const* peer_o, const int32_t* seqlens, void* stream) {
   g_err[0] = 0;
   if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_o)) return fail(-12, "fa_fwd_peers: 0 <= n_peers <= 7 and peer_o non-null");
   if (n_peers > 0 && dtype == FA_DTYPE_F32) return fail(-12, "fa_fwd_peers: peer copies are implemented for the 16-bit and FP8 kernels");
@@ -229,6 +229,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
     p.B = B, p.H = H, p.N = N, p.D = D;
     fill3(p.q_s, q_strides), fill3(p.k_s, k_strides), fill3(p.v_s, v_strides), fill3(p.o_s, o_strides);
     p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
+    p.seqlens = seqlens;
     switch (D) {
       case 16: return launch_fwd32<16>(p, st);
       case 32: return launch_fwd32<32>(p, st);
@@ -254,6 +255,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   p.q_blocks = (N + 255) / 256;
   p.n_peer = n_peers;
   for (int i = 0; i < n_peers; ++i) p.o_peer[i] = peer_o[i];
+  p.seqlens = seqlens;
 #define FA_FWD_CASE(E, DD, C) \
   if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
   FA_FWD_CASE(FA_DTYPE_BF16, 128, true)
@@ -321,7 +323,7 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
   // the single-pass kernel, whose dQ reduction is bound by the SM -> L2 path.
   return fa_bwd_partial(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, D, q_strides,
                         k_strides, v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale,
-                        causal, FA_BWD_DKDV | FA_BWD_DQ, stream);
+                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, stream);
 }
 
 int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
@@ -329,11 +331,12 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
-                   int causal, int which, void* stream) {
+                   int causal, int which, const int32_t* seqlens, void* stream) {
   g_err[0] = 0;
   if (which != FA_BWD_FUSED && ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ))))
     return fail(-10, "fa_bwd_partial: which must be FA_BWD_FUSED or a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
   if (which == FA_BWD_FUSED) {
+    if (seqlens) return fail(-10, "fa_bwd_partial: FA_BWD_FUSED does not take per-batch sequence lengths; use the two-kernel path");
     if (dtype == FA_DTYPE_F32) return fail(-10, "fa_bwd_partial: FA_BWD_FUSED is a 16-bit kernel; float32 uses FA_BWD_DKDV | FA_BWD_DQ");
     const size_t need = fa_bwd_workspace_bytes(B, H, N, D, dtype, causal, FA_BWD_FUSED);
     if (!workspace || workspace_bytes < need)
@@ -364,6 +367,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
     fill3(p.q_s, q_strides), fill3(p.k_s, k_strides), fill3(p.v_s, v_strides), fill3(p.do_s, do_strides);
     fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
     p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
+    p.seqlens = seqlens;
     switch (D) {
       case 16: return launch_bwd32<16>(p, which, st);
       case 32: return launch_bwd32<32>(p, which, st);
@@ -387,6 +391,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   p.B = B, p.H = H, p.N = N;
   fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
   p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e;
+  p.seqlens = seqlens;
 #define FA_BWD_CASE(BF, DD, C)                                                                  \
   if (bf == BF && D == DD && (causal != 0) == C)                                                \
     return which == FA_BWD_FUSED ? launch_bwd16_fused<BF, DD, C>(m, p, workspace, st)           \

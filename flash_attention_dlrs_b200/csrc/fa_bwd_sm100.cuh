@@ -44,6 +44,7 @@ struct BwdParams {
   int B, H, N;
   int64_t dq_s[3], dk_s[3], dv_s[3];  // {sB,sH,sN}
   float scale, scale_log2;
+  const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; see FwdParams::seqlens
 };
 
 template <int kD>
@@ -224,7 +225,11 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = jb * 128;
-  const int n_q_total = (p.N + 127) >> 7;
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
+  if (k0 >= nv) return;   // padded key block: dK / dV rows stay as the caller initialised them
+  // Padded keys inside the last block need no mask here: rows = keys, and a padded key only feeds its own dK / dV rows,
+  // which are never stored.  Padded queries get -L = -inf below, i.e. P = 0.
+  const int n_q_total = (nv + 127) >> 7;
   const int i_begin = kCausal ? jb : 0;
   const int n_it = n_q_total - i_begin;
 
@@ -283,8 +288,8 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = lane * 4 + e;
-        const bool ok = q0 + r < p.N;
-        st[r] = ok ? -lsep[q0 + r] : -INFINITY;  // rows past N: P = exp2(-inf) = 0
+        const bool ok = q0 + r < nv;
+        st[r] = ok ? -lsep[q0 + r] : -INFINITY;  // rows past the valid length: P = exp2(-inf) = 0
         st[128 + r] = ok ? -dlp[q0 + r] : 0.f;
       }
       mbar_arrive(&stat_full[s]);
@@ -387,7 +392,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const int kv_row = k0 + row;
-    const bool in_range = kv_row < p.N;
+    const bool in_range = kv_row < nv;
     if (half == 0) {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dv) + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)kv_row * p.dv_s[2];
       store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base, kD, 1.0f, dst, in_range);
@@ -428,7 +433,13 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int ib = n_blocks - 1 - (int)blockIdx.x;        // heaviest (most key blocks) first under the causal mask
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = ib * 128;
-  const int n_it = kCausal ? ib + 1 : n_blocks;
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
+  if (q0 >= nv) return;   // padded query block
+  const int n_kv_valid = (nv + 127) >> 7;
+  const int n_it = kCausal ? ib + 1 : n_kv_valid;
+  // Non-causal: keys >= nv in the last key block are masked explicitly (padded K rows are real data, not TMA zero fill);
+  // causal: the diagonal mask of the last block already removes them (valid rows are < nv).
+  const bool tail_mask = !kCausal && (nv & 127) != 0;
 
   if (threadIdx.x == 0) {
     mbar_init(&qdo_full, 1);
@@ -576,7 +587,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t tDP = tmem + Cfg::kTmemDP + half * 64 + lane_base;
     const float sl2 = p.scale_log2;
     const int q_row = q0 + row;
-    const bool in_range = q_row < p.N;
+    const bool in_range = q_row < nv;
     const int64_t stat_idx = ((int64_t)b * p.H + h) * p.N + q_row;
     const float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
     const float neg_dl = in_range ? -p.delta[stat_idx] : 0.f;
@@ -613,8 +624,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();
       uint32_t pd[32];
-      if (kCausal && it == n_it - 1)   // key block == query block
+      if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
         dq_elementwise_half<kBf16, true>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd);
+      else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
+        dq_elementwise_half<kBf16, true>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1, half * 64, pd);
       else
         dq_elementwise_half<kBf16, false>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd);
       if (it > 0) mbar_wait(&ds_free[half], (it - 1) & 1);        // dQ MMAs of the previous block have read the box

@@ -51,6 +51,10 @@ struct FwdParams {
   // switch replicates each store; n_peer is then 0.
   void* o_peer[7];
   int n_peer;
+  // Key-padding mask ("masking" on the reference's roadmap, README.md:35-37): seqlens[b] = number of valid tokens of
+  // batch element b (nullptr = all N).  Keys >= seqlens[b] are masked out; query rows >= seqlens[b] are not computed
+  // (their O / L are left untouched: the caller zero-fills).
+  const int* seqlens;
 };
 
 // kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
@@ -99,8 +103,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int qb = p.q_blocks - 1 - (int)blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * 256;
-  const int n_kv_total = (p.N + 127) >> 7;
-  const int ntiles = (p.N - q0 > 128) ? 2 : 1;
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
+  if (q0 >= nv) return;                                              // whole CTA is padding (uniform, before any set-up)
+  const int n_kv_total = (nv + 127) >> 7;
+  const int ntiles = (nv - q0 > 128) ? 2 : 1;
   int nkv[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
@@ -262,9 +268,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
       const int kv0 = j * 128;
       const bool diag = kCausal && (kv0 + 127 > q0 + 128 * t);   // block touches the diagonal
-      const bool ragged = (kv0 + 128 > p.N);
+      const bool ragged = (kv0 + 128 > nv);
       if (diag || ragged) {
-        int limit = p.N - kv0;                         // first invalid column (ragged)
+        int limit = nv - kv0;                          // first invalid column (ragged / padded keys)
         if (kCausal) limit = min(limit, q_row - kv0 + 1);
 #pragma unroll
         for (int c = 0; c < 128; ++c)
@@ -379,7 +385,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_wait(&o_full[t], (my_nkv - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.0f / l;
-      const bool in_range = q_row < p.N;
+      const bool in_range = q_row < nv;
       // Epilogue: O_t / l -> output dtype -> this tile's Q staging buffer (dead since its last S MMA; same size as the O
       // tile) -> global.  Going through shared memory turns "thread = row" into "warp = two full rows": every warp
       // store covers 512 contiguous bytes, which is what makes the peer / multicast copies of the fused all-gather
@@ -432,7 +438,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int it = 0; it < kRowChunks; ++it) {
           const int idx = it * 128 + tid;
           const int r = idx / kRowChunks, ch = idx - r * kRowChunks;
-          if (row0 + r < p.N) {
+          if (row0 + r < nv) {
             uint4 v;
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)

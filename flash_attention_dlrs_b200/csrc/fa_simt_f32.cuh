@@ -27,6 +27,7 @@ struct SimtParams {
   float scale;       // softmax scale
   float scale_log2;  // scale * log2(e)
   int causal;
+  const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; rows past it are loaded as zeros
 };
 
 constexpr int kSimtTile = 64;
@@ -167,11 +168,13 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int qb = gridDim.x - 1 - blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * 64;
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
+  if (q0 >= nv) return;
   const float* qp = p.q + b * p.q_s[0] + h * p.q_s[1];
   const float* kp = p.k + b * p.k_s[0] + h * p.k_s[1];
   const float* vp = p.v + b * p.v_s[0] + h * p.v_s[1];
 
-  simt_load_transposed<kD>(Qt, qp + (int64_t)q0 * p.q_s[2], p.q_s[2], p.N - q0);
+  simt_load_transposed<kD>(Qt, qp + (int64_t)q0 * p.q_s[2], p.q_s[2], nv - q0);
 
   float m[4], l[4], acc[4][kAcc];
 #pragma unroll
@@ -181,12 +184,12 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 #pragma unroll
     for (int j = 0; j < kAcc; ++j) acc[i][j] = 0.f;
   }
-  const int n_kv = p.causal ? min((p.N + 63) / 64, qb + 1) : (p.N + 63) / 64;
+  const int n_kv = p.causal ? min((nv + 63) / 64, qb + 1) : (nv + 63) / 64;
   for (int jb = 0; jb < n_kv; ++jb) {
     const int k0 = jb * 64;
     __syncthreads();  // previous iteration's readers of Kt / Vs / Ps are done (also covers the Qt fill)
-    simt_load_transposed<kD>(Kt, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], p.N - k0);
-    simt_load_rowmajor<kD>(Vs, kD, vp + (int64_t)k0 * p.v_s[2], p.v_s[2], p.N - k0);
+    simt_load_transposed<kD>(Kt, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
+    simt_load_rowmajor<kD>(Vs, kD, vp + (int64_t)k0 * p.v_s[2], p.v_s[2], nv - k0);
     __syncthreads();
     float s[4][4];
     simt_scores_tt<kD>(s, Qt, Kt, ty, tx);
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = k0 + tx * 4 + j;
-        const bool dead = (col >= p.N) || (p.causal && col > row);
+        const bool dead = (col >= nv) || (p.causal && col > row);
         s[i][j] = dead ? -INFINITY : s[i][j] * p.scale_log2;
         mx = fmaxf(mx, s[i][j]);
       }
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
-    if (row >= p.N) continue;
+    if (row >= nv) continue;
     const float inv = 1.0f / l[i];
     float* orow = p.out_o + b * p.o_s[0] + h * p.o_s[1] + (int64_t)row * p.o_s[2];
 #pragma unroll
@@ -276,13 +279,15 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = jb * 64;
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
+  if (k0 >= nv) return;
   const float* qp = p.q + b * p.q_s[0] + h * p.q_s[1];
   const float* dop = p.dout + b * p.do_s[0] + h * p.do_s[1];
   const float* lsep = p.lse + ((int64_t)b * p.H + h) * p.N;
   const float* dlp = p.delta + ((int64_t)b * p.H + h) * p.N;
 
-  simt_load_transposed<kD>(Kt, p.k + b * p.k_s[0] + h * p.k_s[1] + (int64_t)k0 * p.k_s[2], p.k_s[2], p.N - k0);
-  simt_load_transposed<kD>(Vt, p.v + b * p.v_s[0] + h * p.v_s[1] + (int64_t)k0 * p.v_s[2], p.v_s[2], p.N - k0);
+  simt_load_transposed<kD>(Kt, p.k + b * p.k_s[0] + h * p.k_s[1] + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
+  simt_load_transposed<kD>(Vt, p.v + b * p.v_s[0] + h * p.v_s[1] + (int64_t)k0 * p.v_s[2], p.v_s[2], nv - k0);
 
   float dk[4][kAcc], dv[4][kAcc];
 #pragma unroll
@@ -290,12 +295,12 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
 #pragma unroll
     for (int j = 0; j < kAcc; ++j) dk[i][j] = 0.f, dv[i][j] = 0.f;
 
-  const int n_q = (p.N + 63) / 64;
+  const int n_q = (nv + 63) / 64;
   for (int ib = p.causal ? jb : 0; ib < n_q; ++ib) {
     const int q0 = ib * 64;
     __syncthreads();
-    simt_load_rowmajor<kD>(Qs, SS::kLdR, qp + (int64_t)q0 * p.q_s[2], p.q_s[2], p.N - q0);
-    simt_load_rowmajor<kD>(dOs, SS::kLdR, dop + (int64_t)q0 * p.do_s[2], p.do_s[2], p.N - q0);
+    simt_load_rowmajor<kD>(Qs, SS::kLdR, qp + (int64_t)q0 * p.q_s[2], p.q_s[2], nv - q0);
+    simt_load_rowmajor<kD>(dOs, SS::kLdR, dop + (int64_t)q0 * p.do_s[2], p.do_s[2], nv - q0);
     __syncthreads();
     float s[4][4], dp[4][4], lse[4], dl[4];
     simt_scores_rt<kD>(s, Qs, SS::kLdR, Kt, ty, tx);
@@ -303,10 +308,10 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = q0 + ty * 4 + i;
-      lse[i] = row < p.N ? lsep[row] : 0.f;
-      dl[i] = row < p.N ? dlp[row] : 0.f;
+      lse[i] = row < nv ? lsep[row] : 0.f;
+      dl[i] = row < nv ? dlp[row] : 0.f;
     }
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, p.N, p.causal, p.scale_log2);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       *reinterpret_cast<float4*>(Ps + (ty * 4 + i) * kSimtLdT + tx * 4) = make_float4(s[i][0], s[i][1], s[i][2], s[i][3]);
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = k0 + ty * 4 + i;
-    if (row >= p.N) continue;
+    if (row >= nv) continue;
     float* dkrow = p.dk + b * p.dk_s[0] + h * p.dk_s[1] + (int64_t)row * p.dk_s[2];
     float* dvrow = p.dv + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)row * p.dv_s[2];
 #pragma unroll
@@ -353,33 +358,35 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int ib = gridDim.x - 1 - blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = ib * 64;
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
+  if (q0 >= nv) return;
   const float* kp = p.k + b * p.k_s[0] + h * p.k_s[1];
   const float* vp = p.v + b * p.v_s[0] + h * p.v_s[1];
 
-  simt_load_rowmajor<kD>(Qs, SS::kLdR, p.q + b * p.q_s[0] + h * p.q_s[1] + (int64_t)q0 * p.q_s[2], p.q_s[2], p.N - q0);
+  simt_load_rowmajor<kD>(Qs, SS::kLdR, p.q + b * p.q_s[0] + h * p.q_s[1] + (int64_t)q0 * p.q_s[2], p.q_s[2], nv - q0);
   simt_load_rowmajor<kD>(dOs, SS::kLdR, p.dout + b * p.do_s[0] + h * p.do_s[1] + (int64_t)q0 * p.do_s[2], p.do_s[2],
-                         p.N - q0);
+                         nv - q0);
   float lse[4], dl[4], dq[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
-    lse[i] = row < p.N ? p.lse[((int64_t)b * p.H + h) * p.N + row] : 0.f;
-    dl[i] = row < p.N ? p.delta[((int64_t)b * p.H + h) * p.N + row] : 0.f;
+    lse[i] = row < nv ? p.lse[((int64_t)b * p.H + h) * p.N + row] : 0.f;
+    dl[i] = row < nv ? p.delta[((int64_t)b * p.H + h) * p.N + row] : 0.f;
 #pragma unroll
     for (int j = 0; j < kAcc; ++j) dq[i][j] = 0.f;
   }
-  const int n_kv = p.causal ? min((p.N + 63) / 64, ib + 1) : (p.N + 63) / 64;
+  const int n_kv = p.causal ? min((nv + 63) / 64, ib + 1) : (nv + 63) / 64;
   for (int jb = 0; jb < n_kv; ++jb) {
     const int k0 = jb * 64;
     __syncthreads();
-    simt_load_transposed<kD>(Kt, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], p.N - k0);
-    simt_load_transposed<kD>(Vt, vp + (int64_t)k0 * p.v_s[2], p.v_s[2], p.N - k0);
-    simt_load_rowmajor<kD>(Ks, kD, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], p.N - k0);
+    simt_load_transposed<kD>(Kt, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
+    simt_load_transposed<kD>(Vt, vp + (int64_t)k0 * p.v_s[2], p.v_s[2], nv - k0);
+    simt_load_rowmajor<kD>(Ks, kD, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
     __syncthreads();
     float s[4][4], dp[4][4];
     simt_scores_rt<kD>(s, Qs, SS::kLdR, Kt, ty, tx);
     simt_scores_rt<kD>(dp, dOs, SS::kLdR, Vt, ty, tx);
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, p.N, p.causal, p.scale_log2);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(dSs + (ty * 4 + i) * kSimtLdT + tx * 4) =
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
-    if (row >= p.N) continue;
+    if (row >= nv) continue;
     float* dqrow = p.dq + b * p.dq_s[0] + h * p.dq_s[1] + (int64_t)row * p.dq_s[2];
 #pragma unroll
     for (int cc = 0; cc < kAcc / 4; ++cc) {

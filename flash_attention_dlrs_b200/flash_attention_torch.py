@@ -4,6 +4,7 @@ flash_attention_torch.py (FlashAttention :21, FlashAttentionDeterministic :161, 
     O = FlashAttention.apply(Q, K, V)                       # reference call, scale = 1.0, non-causal
     O = FlashAttention.apply(Q, K, V, causal, softmax_scale)  # added trailing arguments, order as in the
                                                               # vendored tutorial (_attention.forward :441)
+    O = FlashAttention.apply(Q, K, V, causal, softmax_scale, seqlens)   # + per-batch valid lengths (key padding)
 
 Differences from the reference, all deliberate:
   * the kernels are hand-written sm_100a CUDA reached through libfa_b200.so (no Triton, no autotune);
@@ -41,15 +42,16 @@ def _validate(Q, K, V):
 class FlashAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool = False,
-                softmax_scale: float = 1.0) -> torch.Tensor:
+                softmax_scale: float = 1.0, seqlens=None) -> torch.Tensor:
         _validate(Q, K, V)
         causal = bool(causal)
         softmax_scale = float(softmax_scale)
-        O, L = _native.forward(Q, K, V, causal, softmax_scale)   # Function.forward runs without graph recording
+        O, L = _native.forward(Q, K, V, causal, softmax_scale, seqlens=seqlens)   # runs without graph recording
         # same saved set as the reference (flash_attention_torch.py:77), unpadded
         ctx.save_for_backward(Q, K, V, O, L)
         ctx.causal = causal
         ctx.softmax_scale = softmax_scale
+        ctx.seqlens = seqlens
         return O
 
     @staticmethod
@@ -58,8 +60,8 @@ class FlashAttention(torch.autograd.Function):
         dO = grad_outputs
         if Q.dtype != dO.dtype:
             raise ValueError("dO must have same dtype as inputs")
-        dQ, dK, dV = _native.backward(Q, K, V, O, dO, L, ctx.causal, ctx.softmax_scale)
-        return dQ, dK, dV, None, None
+        dQ, dK, dV = _native.backward(Q, K, V, O, dO, L, ctx.causal, ctx.softmax_scale, seqlens=ctx.seqlens)
+        return dQ, dK, dV, None, None, None
 
 
 # The reference's second Function differs only in which (broken) backward kernel it launches
@@ -67,6 +69,7 @@ class FlashAttention(torch.autograd.Function):
 FlashAttentionDeterministic = FlashAttention
 
 
-def flash_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0) -> torch.Tensor:
-    """Keyword-friendly front of FlashAttention.apply."""
-    return FlashAttention.apply(Q, K, V, causal, softmax_scale)
+def flash_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0, seqlens=None) -> torch.Tensor:
+    """Keyword-friendly front of FlashAttention.apply.  `seqlens` (B,) int: per-batch valid length (key-padding mask,
+    the "masking" of the reference's roadmap, README.md:35-37); rows beyond it are zero in O and in the gradients."""
+    return FlashAttention.apply(Q, K, V, causal, softmax_scale, seqlens)

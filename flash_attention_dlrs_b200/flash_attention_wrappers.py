@@ -6,7 +6,8 @@ flash_attention_wrappers.py (flash_attention_forward :7, flash_attention_backwar
 
 L is (B, H, N, 1) like the reference's (flash_attention_wrappers.py:38) but float32, in log2 units:
 L = log2(e) * logsumexp_j(softmax_scale * S_ij)  (flash_attention_kernels.py:106).  `deterministic` is accepted
-for signature compatibility and ignored: the backward is always deterministic.
+for signature compatibility and ignored: the backward is always deterministic.  `seqlens` (B,) int, optional, last:
+per-batch valid length (key-padding mask); rows beyond it are zero in O, L and the gradients.
 """
 from __future__ import annotations
 
@@ -27,15 +28,15 @@ def _check(Q, K, V, dev):
         raise NotImplementedError("Q, K, V must be on the same CUDA device")
 
 
-def flash_attention_forward(Q, K, V, dev, causal: bool = False, softmax_scale: float = 1.0):
+def flash_attention_forward(Q, K, V, dev, causal: bool = False, softmax_scale: float = 1.0, seqlens=None):
     _check(Q, K, V, dev)
-    O, L = _native.forward(Q, K, V, bool(causal), float(softmax_scale))
+    O, L = _native.forward(Q, K, V, bool(causal), float(softmax_scale), seqlens=seqlens)
     return O, L.unsqueeze(-1)
 
 
 def flash_attention_backward(Q, K, V, O, dO, L, dev, deterministic: bool = False, causal: bool = False,
-                             softmax_scale: float = 1.0):
+                             softmax_scale: float = 1.0, seqlens=None):
     _check(Q, K, V, dev)
     assert O.shape == Q.shape and dO.shape == Q.shape
     assert dO.dtype == Q.dtype and O.dtype == Q.dtype
-    return _native.backward(Q, K, V, O, dO, L, bool(causal), float(softmax_scale))
+    return _native.backward(Q, K, V, O, dO, L, bool(causal), float(softmax_scale), seqlens=seqlens)

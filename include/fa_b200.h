@@ -51,11 +51,14 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
  * gathered output buffers — NVLink peer-to-peer stores issued by the epilogue warps, overlapped with the remaining tiles.
  * With NVLS, pass a multicast address as `o` and n_peers = 0: the switch replicates each store.  The caller synchronises
  * the ranks (e.g. a barrier on the stream) before anybody reads the gathered buffer.  The reference has no multi-GPU path;
- * this stands where a caller would otherwise follow fa_fwd by an NCCL all-gather of O along H. */
+ * this stands where a caller would otherwise follow fa_fwd by an NCCL all-gather of O along H.
+ * `seqlens` (device pointer to B int32, or NULL) is a key-padding mask — "masking" on the reference's roadmap
+ * (README.md:35-37): batch element b has seqlens[b] valid tokens; keys beyond are masked out, query rows beyond are not
+ * computed and their O / lse are left untouched (the caller zero-fills).  All dtypes. */
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
-                 void* const* peer_o, void* stream);
+                 void* const* peer_o, const int32_t* seqlens, void* stream);
 
 /* Backward preprocess: delta[b,h,i] = sum_d O[b,h,i,d] * dO[b,h,i,d]  (fp32 accumulate).
  * Replaces bwd_D_kernel[grid](...) at flash_attention_torch.py:125-133 and flash_attention_wrappers.py:110-118. */
@@ -82,7 +85,8 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
  * (the dQ kernel, owner = query block, recomputes S and dP) or both — what fa_bwd runs; or FA_BWD_FUSED (16-bit dtypes
  * only): one pass like the reference's bwd_kernel, five matmuls per block pair instead of seven, with dQ accumulated
  * across key blocks by an ORDERED reduction in `workspace` (a turn counter per tile instead of the reference's spin lock,
- * flash_attention_kernels.py:305-320), deterministic as well.  The reference has a single backward launch (flash_attention_torch.py:136-154)
+ * flash_attention_kernels.py:305-320), deterministic as well.  `seqlens` as in fa_fwd_peers (two-kernel path only): gradient
+ * rows beyond seqlens[b] are left untouched (the caller zero-fills).  The reference has a single backward launch (flash_attention_torch.py:136-154)
  * whose dQ part is the spin-locked read-modify-write of flash_attention_kernels.py:305-320; here the two parts are
  * separate kernels, exposed for callers that need only some gradients and for per-kernel timing.  Outputs not
  * selected are left untouched (their pointers must still be valid). */
@@ -94,7 +98,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
-                   int causal, int which, void* stream);
+                   int causal, int which, const int32_t* seqlens, void* stream);
 
 #ifdef __cplusplus
 }

@@ -612,3 +612,71 @@ def test_fused_gather_epilogue_matches_nccl_all_gather_two_gpus():
     """Two ranks (torchrun, NCCL for the rendezvous and the comparison path): the gathered O written by the forward
     kernels' epilogues (NVLS multicast and / or P2P stores) equals forward + NCCL all-gather bit for bit."""
     _run_peer_gather(2, 29917)
+
+
+# ------------------------------------------------------------------------------------------------ key-padding mask
+def _varlen_reference(Q, K, V, dO, lens, scale, causal):
+    """Ground truth for per-batch valid lengths: the oracle on each batch element's first lens[b] tokens, zeros beyond."""
+    ref = {k: torch.zeros(Q.shape, dtype=torch.float64) for k in ("O", "dQ", "dK", "dV")}
+    ref["L"] = torch.zeros(*Q.shape[:3], 1, dtype=torch.float64)
+    for b, n in enumerate(lens):
+        if n == 0:
+            continue
+        r = orc.attention_grads_fp64(Q[b:b + 1, :, :n].float(), K[b:b + 1, :, :n].float(), V[b:b + 1, :, :n].float(),
+                                     dO[b:b + 1, :, :n].float(), scale, causal)
+        for k in ref:
+            ref[k][b:b + 1, :, :n] = r[k]
+    return ref
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_key_padding_mask_per_batch_lengths(dtype, D, causal):
+    """seqlens: every batch element has its own valid length; the padded positions hold arbitrary data (not zeros) and
+    must influence nothing; O / L / gradients beyond the length are zero; backward stays bit-identical."""
+    B, H, N = 5, 2, 384
+    lens = [384, 200, 1, 129, 0]
+    scale = 1.0 / math.sqrt(D)
+    Q, K, V, dO = make_inputs(31, B, H, N, D, dtype)
+    sl = torch.tensor(lens, dtype=torch.int32)
+    q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
+    O, L = flash_attention_forward(q, k, v, DEV, causal, scale, sl)
+    g = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, sl)
+    g2 = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, sl)
+    torch.cuda.synchronize()
+    for a, b in zip(g, g2):
+        assert torch.equal(a, b)
+    ref = _varlen_reference(Q, K, V, dO, lens, scale, causal)
+    tol_o = 1e-4 if dtype == torch.float32 else 2e-3
+    for b, n in enumerate(lens):
+        got_o, want_o = O[b, :, :n].cpu().double(), ref["O"][b, :, :n]
+        if n:
+            slack = 0
+            if dtype != torch.float32:
+                p_absv = orc.reference_sdpa(Q[b:b + 1, :, :n].float(), K[b:b + 1, :, :n].float(),
+                                            V[b:b + 1, :, :n].float().abs(), scale, causal)[0].double()
+                slack = out_half_ulp(want_o, dtype) + 2.0 ** -(MANT_BITS[dtype] + 2) * p_absv
+            assert ((got_o - want_o).abs() <= tol_o + slack).all(), (b, n)
+            assert (L[b, :, :n].cpu().double() - ref["L"][b, :, :n]).abs().max() <= tol_o, (b, n)
+        assert not O[b, :, n:].float().abs().any() and not L[b, :, n:].abs().any(), (b, n)   # padded rows: zero
+    for name, got in zip(("dQ", "dK", "dV"), g):
+        assert rel_err(got.cpu(), ref[name]) <= (1e-4 if dtype == torch.float32 else 1e-2), name
+        for b, n in enumerate(lens):
+            assert not got[b, :, n:].float().abs().any(), (name, b, n)
+
+
+def test_key_padding_mask_autograd_and_full_length_equivalence():
+    """FlashAttention.apply(..., seqlens): gradients flow; seqlens = N everywhere reproduces the unmasked result bitwise."""
+    B, H, N, D = 2, 2, 256, 128
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(33, B, H, N, D, torch.bfloat16))
+    q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+    O = FlashAttention.apply(q, k, v, True, 0.09, torch.tensor([N, N]))
+    O.backward(dO)
+    q2, k2, v2 = (t.clone().requires_grad_(True) for t in (Q, K, V))
+    O2 = FlashAttention.apply(q2, k2, v2, True, 0.09)
+    O2.backward(dO)
+    assert torch.equal(O, O2)
+    for a, b in ((q.grad, q2.grad), (k.grad, k2.grad), (v.grad, v2.grad)):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        FlashAttention.apply(Q, K, V, True, 0.09, torch.tensor([N]))

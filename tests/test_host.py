@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 2
+    assert lib.fa_version() == 3
     assert isinstance(lib.fa_last_error(), bytes)
 
 
