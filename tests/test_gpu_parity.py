@@ -531,6 +531,21 @@ def test_fp8_forward_parity(dtype, causal, N, d):
     assert (L.cpu().double() - ref[1]).abs().max().item() <= 2e-3
 
 
+def test_fp8_forward_with_key_padding_mask():
+    """FP8 forward + per-batch valid lengths: each batch element equals the forward of its own first seqlens[b] tokens
+    bit for bit (same tiles, same arithmetic); the padded rows are zero bytes."""
+    B, H, N, D = 3, 2, 384, 128
+    lens = [384, 130, 77]
+    g = torch.Generator().manual_seed(8)
+    Q, K, V = (torch.randn(B, H, N, D, generator=g).to(torch.float8_e4m3fn).to(DEV) for _ in range(3))
+    O, L = flash_attention_forward(Q, K, V, DEV, True, 0.09, torch.tensor(lens))
+    for b, n in enumerate(lens):
+        Ob, Lb = flash_attention_forward(Q[b:b + 1, :, :n].contiguous(), K[b:b + 1, :, :n].contiguous(),
+                                         V[b:b + 1, :, :n].contiguous(), DEV, True, 0.09)
+        assert torch.equal(O[b:b + 1, :, :n].view(torch.uint8), Ob.view(torch.uint8)) and torch.equal(L[b:b + 1, :, :n], Lb)
+        assert not O[b, :, n:].view(torch.uint8).any() and not L[b, :, n:].any()
+
+
 def test_fp8_is_forward_only_and_deterministic():
     Q, K, V = (torch.randn(1, 2, 256, 128, generator=torch.Generator().manual_seed(s)).to(torch.float8_e5m2).to(DEV)
                for s in (1, 2, 3))

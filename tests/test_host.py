@@ -127,3 +127,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libfa_b200.so")
     with pytest.raises(_lib.FlashAttentionLibraryError, match="no CPU or eager fallback"):
         _lib.load()
+
+
+def test_header_is_plain_c_and_matches_the_library(tmp_path):
+    """include/fa_b200.h must be consumable from C (the drop-in boundary is a C ABI): compile a C translation unit that
+    includes it and takes the address of every declared entry point, then link it against libfa_b200.so."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_check.c"
+    syms = [s for s in _lib.EXPORTED_SYMBOLS]
+    src.write_text('#include "fa_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t p[] = {' +
+                   ", ".join(f"(fn_t){s}" for s in syms) +
+                   '};\n  printf("%d %d\\n", (int)(sizeof p / sizeof p[0]), FA_BWD_FUSED + FA_DTYPE_F8E5M2);\n  return 0;\n}\n')
+    inc = str(_lib.HEADER.parent)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-c", str(src), "-o",
+                    str(tmp_path / "abi_check.o")], check=True, capture_output=True)
+    lib = _lib.LIB_PATH
+    out = subprocess.run([gcc, str(tmp_path / "abi_check.o"), "-L", str(lib.parent), f"-l:{lib.name}", "-o",
+                          str(tmp_path / "abi_check")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]   # every declared symbol resolves against the shared library
