@@ -78,53 +78,100 @@ def ncu_dram_bytes(kernel: str):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and clock-event reasons DURING the timed region: an NVML polling thread (about 1 kHz) whose samples are
+    kept only between mark_begin() and mark_end().  Falls back to `nvidia-smi -lms` when pynvml is unavailable."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, reason bits, watts)
+        self.t0 = self.t1 = None
+        self.handle = self.nvml = self.proc = None
+        self.stop_flag = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                clk = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                bits = int(get_reasons(h))
+                watts = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((time.perf_counter(), clk, bits, watts))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.0005)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
+    def _pump(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
+        inv = {v: k for k, v in self.REASONS.items()}
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                smax = float(parts[1])
+                clk, self.smax, watts = float(parts[0]), float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            bits = sum(inv[nm] for nm, val in zip(names, parts[3:7]) if val.lower().startswith("active"))
+            self.samples.append((time.perf_counter(), clk, bits, watts))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML / nvidia-smi unavailable"]}
+        time.sleep(0.01)
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or x[0])]
+        used = inside if inside else self.samples
+        bits = 0
+        for x in used:
+            bits |= x[2]
+        return {"sm_mhz": statistics.median(x[1] for x in used) if used else None, "sm_max_mhz": getattr(self, "smax", None),
+                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k),
+                "power_w": statistics.median(x[3] for x in used) if used else None,
+                "samples": len(inside), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -227,14 +274,16 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
