@@ -31,6 +31,9 @@ EXPORTED_SYMBOLS = (
     "fa_bwd_workspace_bytes",
     "fa_bwd",
     "fa_bwd_partial",
+    "fa_merge_partial",
+    "fa_accumulate",
+    "fa_round_rows",
 )
 
 
@@ -105,6 +108,16 @@ def _declare(lib):
                                    i, vp, vp]
 
 
+def _declare_ring(lib):
+    vp, i, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    lib.fa_merge_partial.restype = i
+    lib.fa_merge_partial.argtypes = [vp, vp, vp, vp, ll, i, i, i, vp]
+    lib.fa_accumulate.restype = i
+    lib.fa_accumulate.argtypes = [vp, vp, ll, i, i, vp]
+    lib.fa_round_rows.restype = i
+    lib.fa_round_rows.argtypes = [vp, vp, ll, i, vp]
+
+
 def load():
     """Return the ctypes handle of libfa_b200.so (loaded once per process).  Never builds implicitly."""
     global _lib
@@ -125,6 +138,7 @@ def load():
                 if not hasattr(lib, sym):
                     raise FlashAttentionLibraryError(f"{LIB_PATH} does not export {sym}")
             _declare(lib)
+            _declare_ring(lib)
             _lib = lib
     return _lib
 

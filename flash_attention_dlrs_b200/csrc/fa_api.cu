@@ -5,6 +5,7 @@
 #include "fa_bwd_fused_sm100.cuh"
 #include "fa_bwd_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
+#include "fa_merge.cuh"
 #include "fa_preprocess.cuh"
 #include "fa_simt_f32.cuh"
 #include "tmap.h"
@@ -406,6 +407,71 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   FA_BWD_CASE(false, 64, false)
 #undef FA_BWD_CASE
   return fail(-3, "fa_bwd: no kernel for dtype %d D %d", dtype, D);
+}
+
+// ---------------------------------------------------------------------------------------------- ring attention helpers
+static int check_rows(const char* fn, long long rows, int D, int dtype) {
+  if (rows <= 0 || D <= 0 || D % 8 != 0 || D > 256) return fail(-1, "%s: rows > 0 and D a multiple of 8, <= 256 (got %lld, %d)", fn, rows, D);
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16) return fail(-2, "%s: 16-bit partials only (dtype %d)", fn, dtype);
+  if (256 % (D / 8) != 0 || D / 8 > 32) return fail(-3, "%s: D / 8 must divide 256 and be <= 32 (D = %d)", fn, D);
+  return 0;
+}
+static unsigned grid_for(long long work_items) {
+  long long g = (work_items + 255) / 256;
+  return (unsigned)(g < 1 ? 1 : (g > 148LL * 16 ? 148LL * 16 : g));
+}
+
+int fa_merge_partial(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part, long long rows, int D,
+                     int dtype, int first, void* stream) {
+  g_err[0] = 0;
+  if (int r = check_rows("fa_merge_partial", rows, D, dtype)) return r;
+  if (!o_acc || !lse_acc || !o_part || !lse_part) return fail(-6, "fa_merge_partial: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tpr = D / 8;
+  const unsigned grid = grid_for(rows * tpr);
+  const uint16_t* part = static_cast<const uint16_t*>(o_part);
+#define FA_MERGE_CASE(T)                                                                                              \
+  if (tpr == T) {                                                                                                     \
+    if (dtype == FA_DTYPE_BF16)                                                                                       \
+      fa::fa_merge_partial_kernel<true, T><<<grid, 256, 0, st>>>(o_acc, lse_acc, part, lse_part, rows, first);        \
+    else                                                                                                              \
+      fa::fa_merge_partial_kernel<false, T><<<grid, 256, 0, st>>>(o_acc, lse_acc, part, lse_part, rows, first);       \
+    cudaError_t e = cudaGetLastError();                                                                               \
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fa_merge_partial launch");                                            \
+  }
+  FA_MERGE_CASE(1) FA_MERGE_CASE(2) FA_MERGE_CASE(4) FA_MERGE_CASE(8) FA_MERGE_CASE(16) FA_MERGE_CASE(32)
+#undef FA_MERGE_CASE
+  return fail(-3, "fa_merge_partial: no kernel for D %d", D);
+}
+
+int fa_accumulate(float* acc, const void* part, long long n, int dtype, int first, void* stream) {
+  g_err[0] = 0;
+  if (n <= 0 || n % 8 != 0) return fail(-1, "fa_accumulate: n must be a positive multiple of 8 (got %lld)", n);
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16) return fail(-2, "fa_accumulate: 16-bit partials only (dtype %d)", dtype);
+  if (!acc || !part) return fail(-6, "fa_accumulate: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint16_t* p16 = static_cast<const uint16_t*>(part);
+  if (dtype == FA_DTYPE_BF16)
+    fa::fa_accumulate_kernel<true><<<grid_for(n / 8), 256, 0, st>>>(acc, p16, n / 8, first);
+  else
+    fa::fa_accumulate_kernel<false><<<grid_for(n / 8), 256, 0, st>>>(acc, p16, n / 8, first);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "fa_accumulate launch");
+}
+
+int fa_round_rows(void* out, const float* in, long long n, int dtype, void* stream) {
+  g_err[0] = 0;
+  if (n <= 0 || n % 8 != 0) return fail(-1, "fa_round_rows: n must be a positive multiple of 8 (got %lld)", n);
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16) return fail(-2, "fa_round_rows: 16-bit output only (dtype %d)", dtype);
+  if (!out || !in) return fail(-6, "fa_round_rows: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* o16 = static_cast<uint16_t*>(out);
+  if (dtype == FA_DTYPE_BF16)
+    fa::fa_round_kernel<true><<<grid_for(n / 8), 256, 0, st>>>(o16, in, n / 8);
+  else
+    fa::fa_round_kernel<false><<<grid_for(n / 8), 256, 0, st>>>(o16, in, n / 8);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "fa_round_rows launch");
 }
 
 }  // extern "C"

@@ -100,6 +100,19 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, const int32_t* seqlens, void* stream);
 
+/* Sequence-parallel (ring) attention helpers — no counterpart in the reference (single GPU); they sit where a caller that
+ * shards the SEQUENCE across GPUs combines what fa_fwd / fa_bwd return for one key / value shard at a time.
+ * All buffers contiguous; 16-bit partials (dtype 0 / 1), fp32 accumulators.
+ *   fa_merge_partial: (o_acc, lse_acc) <- exact combination with the partial (o_part, lse_part) of another key shard:
+ *     L = log2(2^La + 2^Lp), O = Oa 2^(La-L) + Op 2^(Lp-L); rows x D, lse per row (log2 units, -inf = nothing seen);
+ *     first != 0 initialises the accumulators from the partial.
+ *   fa_accumulate:    acc (+)= part  (n elements, n % 8 == 0); first != 0 overwrites.
+ *   fa_round_rows:    out (16-bit, round to nearest even) = in (fp32). */
+int fa_merge_partial(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part, long long rows, int D,
+                     int dtype, int first, void* stream);
+int fa_accumulate(float* acc, const void* part, long long n, int dtype, int first, void* stream);
+int fa_round_rows(void* out, const float* in, long long n, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
