@@ -114,6 +114,8 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
+    if Q.numel() == 0 and out is None:   # empty batch / no heads / no tokens: nothing to launch
+        return torch.empty_like(Q), torch.empty((B, H, N), dtype=torch.float32, device=Q.device)
     d_run = padded_head_dim(d, Q.dtype)
     q, k, v = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V))
     sl, sl_ptr = _seqlens_arg(seqlens, B, Q.device)
@@ -169,6 +171,8 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
     code = dtype_code(Q.dtype)
     if Q.dtype in FP8_DTYPES:
         raise TypeError(f"dtype {Q.dtype} not supported in backward (the FP8 path is forward-only).")
+    if Q.numel() == 0:
+        return torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
     d_run = padded_head_dim(d, Q.dtype)
     q, k, v, o, do = (_kernel_ready(_pad_d(t, d_run)) for t in (Q, K, V, O, dO))
     lse = L if (L.dtype == torch.float32 and L.is_contiguous()) else L.to(torch.float32).contiguous()  # (B,H,N[,1])

@@ -769,3 +769,34 @@ def test_ring_attention_two_gpus():
     for line in lines:
         res = json.loads(line)
         assert res["ok"], res
+
+
+# ------------------------------------------------------------------------------------------------ extremes
+@pytest.mark.parametrize("shape", [(0, 4, 128, 64), (2, 0, 128, 64), (2, 4, 0, 64)])
+def test_empty_inputs_return_empty_outputs(shape):
+    Q = torch.empty(shape, dtype=torch.bfloat16, device=DEV)
+    O, L = flash_attention_forward(Q, Q, Q, DEV, True, 0.1)
+    assert O.shape == Q.shape and L.shape == (*shape[:3], 1)
+    g = flash_attention_backward(Q, Q, Q, O, Q, L, DEV, False, True, 0.1)
+    assert all(t.shape == Q.shape for t in g)
+
+
+def test_long_ragged_sequence_against_an_independent_gpu_implementation():
+    """N = 65536 + 77 (ragged, 513 key blocks), too large for the fp64 oracle: cross-check against torch's own flash
+    SDPA on the GPU (an independent implementation; looser tolerance than the oracle tests), and bit-identical reruns."""
+    B, H, N, D = 1, 2, 65536 + 77, 128
+    scale = D ** -0.5
+    g = torch.Generator(device=DEV).manual_seed(5)
+    Q, K, V, dO = (torch.randn(B, H, N, D, generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16) for _ in range(4))
+    O, L = flash_attention_forward(Q, K, V, DEV, True, scale)
+    grads = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, scale)
+    again = flash_attention_backward(Q, K, V, O, dO, L, DEV, False, True, scale)
+    for a, b in zip(grads, again):
+        assert torch.equal(a, b)
+    q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale)
+    rg = torch.autograd.grad(ref, (q, k, v), dO)
+    assert (O.float() - ref.float()).abs().max().item() <= 3e-2
+    for name, a, b in zip(("dQ", "dK", "dV"), grads, rg):
+        assert rel_err(a.cpu(), b.detach().cpu()) <= 2e-2, name
+    assert torch.isfinite(L).all()
