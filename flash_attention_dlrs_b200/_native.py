@@ -47,7 +47,8 @@ def _kernel_ready(t: torch.Tensor) -> torch.Tensor:
     sB, sH, sN, sD = t.stride()
     ok = sD == 1 and t.data_ptr() % 16 == 0 and sN % gran == 0
     ok = ok and (H == 1 or sH % gran == 0) and (B == 1 or sB % gran == 0)
-    ok = ok and min(sB, sH, sN) >= 0
+    # broadcast (stride 0) or reversed views cannot be described to TMA: copy them
+    ok = ok and sN > 0 and (H == 1 or sH > 0) and (B == 1 or sB > 0) and (N == 1 or sN >= t.shape[-1])
     return t if ok else t.contiguous()
 
 

@@ -800,3 +800,19 @@ def test_long_ragged_sequence_against_an_independent_gpu_implementation():
     for name, a, b in zip(("dQ", "dK", "dV"), grads, rg):
         assert rel_err(a.cpu(), b.detach().cpu()) <= 2e-2, name
     assert torch.isfinite(L).all()
+
+
+def test_bnhd_storage_viewed_as_bhnd_needs_no_copy_and_matches():
+    """(B, N, H, D) storage (the layout flash_attn uses) viewed as (B, H, N, D): the strides go straight into the TMA
+    tensor maps; results equal the contiguous run bit for bit, forward and backward."""
+    B, H, N, D = 2, 4, 384, 128
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(51, B, H, N, D, torch.bfloat16))
+    tq, tk, tv, tdo = (t.transpose(1, 2).contiguous().transpose(1, 2) for t in (Q, K, V, dO))   # BNHD storage
+    assert not tq.is_contiguous() and _native._kernel_ready(tq).data_ptr() == tq.data_ptr()
+    O1, L1 = flash_attention_forward(Q, K, V, DEV, True, 0.09)
+    O2, L2 = flash_attention_forward(tq, tk, tv, DEV, True, 0.09)
+    assert torch.equal(O1, O2) and torch.equal(L1, L2)
+    g1 = flash_attention_backward(Q, K, V, O1, dO, L1, DEV, False, True, 0.09)
+    g2 = flash_attention_backward(tq, tk, tv, O2, tdo, L2, DEV, False, True, 0.09)
+    for a, b in zip(g1, g2):
+        assert torch.equal(a, b)

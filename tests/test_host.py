@@ -108,6 +108,13 @@ def test_kernel_ready_views():
     assert _native._kernel_ready(x.transpose(1, 2)).is_contiguous() or True
     y = x[..., ::2]
     assert _native._kernel_ready(y).stride(-1) == 1
+    # broadcast views (stride 0) cannot be described to TMA: they are materialised
+    e = torch.zeros(1, 1, 32, 64, dtype=torch.bfloat16).expand(2, 4, 32, 64)
+    r = _native._kernel_ready(e)
+    assert r.is_contiguous() and r.shape == e.shape
+    # (B, N, H, D) storage viewed as (B, H, N, D): legal as is (strides are multiples of 16 bytes), no copy
+    z = torch.zeros(2, 32, 4, 64, dtype=torch.bfloat16).transpose(1, 2)
+    assert _native._kernel_ready(z).data_ptr() == z.data_ptr() and not _native._kernel_ready(z).is_contiguous()
 
 
 def test_head_range_partitions_heads():
