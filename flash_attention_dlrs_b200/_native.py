@@ -101,8 +101,26 @@ def _seqlens_arg(seqlens, B: int, device):
     return t, _ptr(t)
 
 
+def dropout_threshold(dropout_p: float) -> int:
+    """The kernels' quantisation of a dropout probability: an entry is dropped with probability threshold / 256
+    (fa_dropout.cuh); 0 = no dropout."""
+    p = float(dropout_p)
+    if not 0.0 <= p < 1.0:
+        raise ValueError(f"dropout_p must be in [0, 1), got {dropout_p}")
+    return min(int(p * 256.0 + 0.5), 255)
+
+
+def _dropout_args(dropout_p, dropout_seed):
+    p = float(dropout_p)
+    if dropout_threshold(p) == 0:
+        return 0.0, 0
+    if dropout_seed is None:
+        raise ValueError("dropout_p > 0 needs a dropout_seed (the backward regenerates the mask from it)")
+    return p, int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+
+
 def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float, out=None,
-            peer_ptrs=(), seqlens=None):
+            peer_ptrs=(), seqlens=None, dropout_p: float = 0.0, dropout_seed=None):
     """O (B,H,N,d) in the input dtype and L (B,H,N) float32 in log2 units.  Inputs already validated.
 
     `out` = (data_ptr, element strides (sB, sH, sN, 1)) makes the kernel write O at a caller-owned address (a window of
@@ -111,10 +129,17 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
     O = None.
 
     `seqlens` (B,) int: key-padding mask — batch element b has seqlens[b] valid tokens; keys beyond are masked out and
-    the rows of O / L beyond are zero."""
+    the rows of O / L beyond are zero.
+
+    `dropout_p`, `dropout_seed`: in-kernel dropout of the attention probabilities (16-bit and float32; quantised to
+    dropout_threshold(p) / 256, kept entries scaled by the reciprocal of the keep rate).  The mask is a pure function
+    of (seed, b, h, query, key) — oracle/attention_oracle.py restates it; L is that of the undropped scores."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
+    drop_p, drop_seed = _dropout_args(dropout_p, dropout_seed)
+    if drop_p and Q.dtype in FP8_DTYPES:
+        raise TypeError(f"dropout is not implemented for the FP8 forward ({Q.dtype})")
     if Q.numel() == 0 and out is None:   # empty batch / no heads / no tokens: nothing to launch
         return torch.empty_like(Q), torch.empty((B, H, N), dtype=torch.float32, device=Q.device)
     d_run = padded_head_dim(d, Q.dtype)
@@ -136,7 +161,7 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
         rc = lib.fa_fwd_peers(_ptr(q), _ptr(k), _ptr(v), o_ptr, _ptr(L), B, H, N, d_run,
                               _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), o_strides,
                               code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers, sl_ptr,
-                              _stream_ptr(Q.device))
+                              drop_p, drop_seed, _stream_ptr(Q.device))
     _lib.check(rc, "fa_fwd")
     if O is None:
         return None, L
@@ -161,15 +186,17 @@ BWD_DKDV, BWD_DQ, BWD_FUSED = 1, 2, 4
 
 
 def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int | None = None, delta=None,
-             seqlens=None):
+             seqlens=None, dropout_p: float = 0.0, dropout_seed=None):
     """dQ, dK, dV (B,H,N,d) in the input dtype; deterministic (bit-identical across runs).
     `which` = None runs what fa_bwd runs: the two-kernel path (BWD_DKDV | BWD_DQ; either half can be selected alone,
     unselected outputs are uninitialised).  BWD_FUSED selects the single-pass kernel with the ordered dQ reduction
     (16-bit inputs only).  `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch.
-    `seqlens` as in forward(): gradient rows beyond seqlens[b] are zero (two-kernel path only)."""
+    `seqlens` as in forward(): gradient rows beyond seqlens[b] are zero (two-kernel path only).
+    `dropout_p`, `dropout_seed`: the values the forward ran with (two-kernel path only)."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
+    drop_p, drop_seed = _dropout_args(dropout_p, dropout_seed)
     if Q.dtype in FP8_DTYPES:
         raise TypeError(f"dtype {Q.dtype} not supported in backward (the FP8 path is forward-only).")
     if Q.numel() == 0:
@@ -194,7 +221,7 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
                                 d_run, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),
                                 _lib.strides4(dQ), _lib.strides4(dK), _lib.strides4(dV),
                                 code, float(softmax_scale), int(bool(causal)), int(which), sl_ptr,
-                                _stream_ptr(Q.device))
+                                drop_p, drop_seed, _stream_ptr(Q.device))
     _lib.check(rc, "fa_bwd")
     if d_run != d:
         dQ, dK, dV = dQ[..., :d], dK[..., :d], dV[..., :d]

@@ -66,16 +66,31 @@ int set_smem(K kernel, int bytes) {
   return 0;
 }
 
+// dropout_p -> DropParams (fa_dropout.cuh): the probability is quantised to 1/256; 0 (or anything that rounds to 0) = off
+int make_drop(const char* fn, float dropout_p, uint64_t seed, fa::DropParams* d) {
+  *d = fa::DropParams{0u, 0u, 0u, 1.0f};
+  if (!(dropout_p >= 0.f) || !(dropout_p < 1.f)) return fail(-13, "%s: dropout_p must be in [0, 1) (got %g)", fn, (double)dropout_p);
+  long t = lroundf(dropout_p * 256.0f);
+  if (t > 255) t = 255;
+  d->thresh = (uint32_t)t;
+  d->seed_lo = (uint32_t)seed, d->seed_hi = (uint32_t)(seed >> 32);
+  d->rp = 256.0f / (float)(256 - t);
+  return 0;
+}
+
 void fill3(int64_t (&dst)[3], const int64_t s[4]) {
   dst[0] = s[0], dst[1] = s[1], dst[2] = s[2];
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <int kElt, int kD, bool kCausal>
+template <int kElt, int kD, bool kCausal, bool kDrop = false>
 int launch_fwd16(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p, int H,
                  int B, cudaStream_t st) {
   using Cfg = fa::FwdCfg<kD, kElt>;
-  auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal>;
+  if constexpr (kElt < 3 && !kDrop) {
+    if (p.drop.thresh) return launch_fwd16<kElt, kD, kCausal, true>(tq, tk, tv, p, H, B, st);
+  }
+  auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal, kDrop>;
   if (int r = set_smem(kern, Cfg::kSmemBytes)) return r;
   dim3 grid(p.q_blocks, H, B);
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
@@ -118,10 +133,13 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------- backward (16-bit)
-template <bool kBf16, int kD, bool kCausal>
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false>
 int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaStream_t st) {
+  if constexpr (!kDrop) {
+    if (p.drop.thresh) return launch_bwd16<kBf16, kD, kCausal, true>(m, p, which, st);
+  }
   if (which & FA_BWD_DKDV) {
-    auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal>;
+    auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal, kDrop>;
     if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDkdv)) return r;
     dim3 grid((p.N + 127) / 128, p.H, p.B);
     kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDkdv, st>>>(m.q, m.k, m.v, m.dout, p);
@@ -129,7 +147,7 @@ int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaSt
     if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(dK/dV) launch");
   }
   if (which & FA_BWD_DQ) {
-    auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal>;
+    auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal, kDrop>;
     if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDq)) return r;
     dim3 grid((p.N + 127) / 128, p.H, p.B);
     kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDq, st>>>(m.q, m.k, m.v, m.dout, p);
@@ -194,7 +212,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 3; }
+int fa_version(void) { return 4; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -202,14 +220,18 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
   return fa_fwd_peers(q, k, v, o, lse, B, H, N, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale,
-                      causal, 0, nullptr, nullptr, stream);
+                      causal, 0, nullptr, nullptr, 0.f, 0, stream);
 }
 
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
-                 void* const* peer_o, const int32_t* seqlens, void* stream) {
+                 void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed, void* stream) {
   g_err[0] = 0;
+  fa::DropParams drop;
+  if (int r = make_drop("fa_fwd_peers", dropout_p, dropout_seed, &drop)) return r;
+  if (drop.thresh && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
+    return fail(-13, "fa_fwd_peers: dropout is not implemented for the FP8 forward");
   if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_o)) return fail(-12, "fa_fwd_peers: 0 <= n_peers <= 7 and peer_o non-null");
   if (n_peers > 0 && dtype == FA_DTYPE_F32) return fail(-12, "fa_fwd_peers: peer copies are implemented for the 16-bit and FP8 kernels");
   for (int i = 0; i < n_peers; ++i)
@@ -231,6 +253,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
     fill3(p.q_s, q_strides), fill3(p.k_s, k_strides), fill3(p.v_s, v_strides), fill3(p.o_s, o_strides);
     p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
     p.seqlens = seqlens;
+    p.drop = drop;
     switch (D) {
       case 16: return launch_fwd32<16>(p, st);
       case 32: return launch_fwd32<32>(p, st);
@@ -257,6 +280,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   p.n_peer = n_peers;
   for (int i = 0; i < n_peers; ++i) p.o_peer[i] = peer_o[i];
   p.seqlens = seqlens;
+  p.drop = drop;
 #define FA_FWD_CASE(E, DD, C) \
   if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
   FA_FWD_CASE(FA_DTYPE_BF16, 128, true)
@@ -324,7 +348,7 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
   // the single-pass kernel, whose dQ reduction is bound by the SM -> L2 path.
   return fa_bwd_partial(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, D, q_strides,
                         k_strides, v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale,
-                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, stream);
+                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, 0.f, 0, stream);
 }
 
 int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
@@ -332,8 +356,13 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
-                   int causal, int which, const int32_t* seqlens, void* stream) {
+                   int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                   void* stream) {
   g_err[0] = 0;
+  fa::DropParams drop;
+  if (int r = make_drop("fa_bwd_partial", dropout_p, dropout_seed, &drop)) return r;
+  if (drop.thresh && which == FA_BWD_FUSED)
+    return fail(-13, "fa_bwd_partial: FA_BWD_FUSED has no dropout; use the two-kernel path");
   if (which != FA_BWD_FUSED && ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ))))
     return fail(-10, "fa_bwd_partial: which must be FA_BWD_FUSED or a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
   if (which == FA_BWD_FUSED) {
@@ -369,6 +398,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
     fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
     p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
     p.seqlens = seqlens;
+    p.drop = drop;
     switch (D) {
       case 16: return launch_bwd32<16>(p, which, st);
       case 32: return launch_bwd32<32>(p, which, st);
@@ -393,6 +423,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
   p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e;
   p.seqlens = seqlens;
+  p.drop = drop;
 #define FA_BWD_CASE(BF, DD, C)                                                                  \
   if (bf == BF && D == DD && (causal != 0) == C)                                                \
     return which == FA_BWD_FUSED ? launch_bwd16_fused<BF, DD, C>(m, p, workspace, st)           \

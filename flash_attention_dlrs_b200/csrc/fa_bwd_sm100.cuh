@@ -22,6 +22,7 @@
 //   warps 0-7  elementwise (P, dS) + epilogue      warp 8  TMA producer (+ row statistics)     warp 9  MMA issuer
 #pragma once
 
+#include "fa_dropout.cuh"
 #include "sm100_ptx.cuh"
 
 // Share of the exponentials computed on the FMA pipe instead of MUFU (bit i = column pair i of every 8).  Off: the
@@ -45,6 +46,7 @@ struct BwdParams {
   int64_t dq_s[3], dk_s[3], dv_s[3];  // {sB,sH,sN}
   float scale, scale_log2;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; see FwdParams::seqlens
+  DropParams drop;     // dropout of the attention probabilities (kDrop instantiations only), fa_dropout.cuh
 };
 
 template <int kD>
@@ -93,9 +95,16 @@ __device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float 
 // (FFMA2 / FADD2 / FMUL2).  kColStats: -L and -delta vary along the columns and come from shared memory (dK/dV
 // kernel, transposed scores); otherwise they are per-thread constants (dQ kernel).  kMask: causal diagonal block.
 // kStoreP: the dK/dV kernel needs P^T (for dV); the dQ kernel only needs dS, stored over S.
-template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP>
+// kDrop: dropout — the stored P is keep o P (its 1 / (1 - p) goes into the dV epilogue) and dS = P o (keep * rp * dP - delta);
+// `drop_word` = key + word index of this thread's first element pair, `drop_shift` / kDropSecond as in fa_dropout.cuh,
+// consecutive pairs are kDropStep words apart.
+template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP, bool kDrop = false>
 __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
-                                                     uint64_t nd_c, float sl2, int row, int col0) {
+                                                     uint64_t nd_c, float sl2, int row, int col0,
+                                                     uint32_t drop_word = 0, uint32_t drop_shift = 0,
+                                                     uint32_t drop_thresh = 0, float drop_rp = 1.f) {
+  constexpr uint32_t kDropStep = kTransposed ? (1u << 15) : 1u;
+  constexpr int kDropSecond = kTransposed ? 16 : 8;
 #if FA_ABLATE == 3
   return;
 #endif
@@ -140,8 +149,16 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
           if (kTransposed ? (row > c0 + 1) : (c0 + 1 > row)) p1 = 0.f;
         }
         float d0, d1;
-        f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd4[u])), d0, d1);
-        if constexpr (kStoreP) pp[g] = pack2<kBf16>(p0, p1);
+        if constexpr (kDrop) {
+          bool keep0, keep1;
+          drop_keep_pair<kDropSecond>(drop_word + (uint32_t)(e >> 1) * kDropStep, drop_shift, drop_thresh, keep0, keep1);
+          const uint64_t f2 = f32x2_pack(keep0 ? drop_rp : 0.f, keep1 ? drop_rp : 0.f);
+          f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_fma(f32x2_pack_bits(dr[e], dr[e + 1]), f2, nd4[u])), d0, d1);
+          if constexpr (kStoreP) pp[g] = pack2<kBf16>(keep0 ? p0 : 0.f, keep1 ? p1 : 0.f);
+        } else {
+          f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd4[u])), d0, d1);
+          if constexpr (kStoreP) pp[g] = pack2<kBf16>(p0, p1);
+        }
         pd[g] = pack2<kBf16>(d0, d1);
       }
     }
@@ -157,9 +174,11 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
 // dQ kernel flavour: per-thread statistics, dS only.  The two score accumulators are copied to registers first and
 // released to the MMA warp (`sc_free`) before any arithmetic, so the next block's score MMAs overlap this stage.
 // Output: 64 values of this thread's row as 32 packed 16-bit pairs in `pd`.
-template <bool kBf16, bool kMask>
+template <bool kBf16, bool kMask, bool kDrop = false>
 __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
-                                                    uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32]) {
+                                                    uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32],
+                                                    uint32_t drop_word = 0, uint32_t drop_shift = 0,
+                                                    uint32_t drop_thresh = 0, float drop_rp = 1.f) {
   uint32_t sr[64], dr[64];
   tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
   tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
@@ -195,13 +214,20 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
       if (c0 + 1 > row) p1 = 0.f;
     }
     float d0, d1;
-    f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd)), d0, d1);
+    if constexpr (kDrop) {   // dS = P o (keep * rp * dP - delta); row walk, one word per key pair
+      bool keep0, keep1;
+      drop_keep_pair<8>(drop_word + (uint32_t)g, drop_shift, drop_thresh, keep0, keep1);
+      const uint64_t f2 = f32x2_pack(keep0 ? drop_rp : 0.f, keep1 ? drop_rp : 0.f);
+      f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_fma(f32x2_pack_bits(dr[e], dr[e + 1]), f2, nd)), d0, d1);
+    } else {
+      f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd)), d0, d1);
+    }
     pd[g] = pack2<kBf16>(d0, d1);
   }
 }
 
 // ================================================================================================ dK / dV
-template <bool kBf16, int kD, bool kCausal>
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false>
 __global__ void __launch_bounds__(384, 1)
 fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -372,6 +398,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tS = tmem + Cfg::kTmemS + half * 64 + lane_base;
     const uint32_t tDP = tmem + Cfg::kTmemDP + half * 64 + lane_base;
     const float sl2 = p.scale_log2;
+    // dropout: this thread walks column (key) k0 + row of the mask, one hash per pair of queries (fa_dropout.cuh)
+    uint32_t drop_col = 0, drop_shift = 0;
+    if constexpr (kDrop) {
+      drop_col = drop_key(p.drop, b * p.H + h) + drop_word_index(half * 64, k0 + row);
+      drop_shift = 8u * ((k0 + row) & 1);
+    }
 
     for (int it = 0; it < n_it; ++it) {
       const int s = it % NS;
@@ -379,10 +411,13 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&sc_full[half], it & 1);
       tc_fence_after();
       const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
+      const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
       if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
-        bwd_elementwise_half<kBf16, true, true, true, true>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64);
+        bwd_elementwise_half<kBf16, true, true, true, true, kDrop>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
+                                                                   drop_shift, p.drop.thresh, p.drop.rp);
       else
-        bwd_elementwise_half<kBf16, true, false, true, true>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64);
+        bwd_elementwise_half<kBf16, true, false, true, true, kDrop>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
+                                                                    drop_shift, p.drop.thresh, p.drop.rp);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[half]);
@@ -395,7 +430,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool in_range = kv_row < nv;
     if (half == 0) {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dv) + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)kv_row * p.dv_s[2];
-      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base, kD, 1.0f, dst, in_range);
+      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base, kD, kDrop ? p.drop.rp : 1.0f, dst, in_range);
     } else {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dk) + b * p.dk_s[0] + h * p.dk_s[1] + (int64_t)kv_row * p.dk_s[2];
       store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc1 + lane_base, kD, p.scale, dst, in_range);
@@ -408,7 +443,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ================================================================================================ dQ
-template <bool kBf16, int kD, bool kCausal>
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false>
 __global__ void __launch_bounds__(384, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -592,6 +627,12 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
     const float neg_dl = in_range ? -p.delta[stat_idx] : 0.f;
     const uint64_t nl2 = f32x2_pack(neg_lse, neg_lse), nd2 = f32x2_pack(neg_dl, neg_dl);
+    // dropout: this thread walks row q_row of the mask, one hash per pair of keys (fa_dropout.cuh)
+    uint32_t drop_row = 0, drop_shift = 0;
+    if constexpr (kDrop) {
+      drop_row = drop_key(p.drop, b * p.H + h) + drop_word_index(q_row, half * 64);
+      drop_shift = 16u * (q_row & 1);
+    }
 
     // Stationary operands: warpgroup a moves Q_i, warpgroup b moves dO_i from the (swizzled) TMA tile into TMEM,
     // row r -> lane r, elements (2c, 2c+1) -> column c.  As TMEM A operands they cost no shared-memory bandwidth
@@ -624,12 +665,16 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();
       uint32_t pd[32];
+      const uint32_t dw = drop_row + (uint32_t)(it * 64);
       if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
-        dq_elementwise_half<kBf16, true>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd);
+        dq_elementwise_half<kBf16, true, kDrop>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw, drop_shift,
+                                                p.drop.thresh, p.drop.rp);
       else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
-        dq_elementwise_half<kBf16, true>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1, half * 64, pd);
+        dq_elementwise_half<kBf16, true, kDrop>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1, half * 64, pd,
+                                                dw, drop_shift, p.drop.thresh, p.drop.rp);
       else
-        dq_elementwise_half<kBf16, false>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd);
+        dq_elementwise_half<kBf16, false, kDrop>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
+                                                 drop_shift, p.drop.thresh, p.drop.rp);
       if (it > 0) mbar_wait(&ds_free[half], (it - 1) & 1);        // dQ MMAs of the previous block have read the box
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)

@@ -20,6 +20,7 @@
 // The O rescale is lazy: a warp rewrites its O rows only when a row max grew by more than 2^8.
 #pragma once
 
+#include "fa_dropout.cuh"
 #include "sm100_ptx.cuh"
 
 // Which of every 8 consecutive column pairs compute exp2 with the FMA-pipe polynomial instead of MUFU (bit i = pair i).
@@ -55,6 +56,8 @@ struct FwdParams {
   // batch element b (nullptr = all N).  Keys >= seqlens[b] are masked out; query rows >= seqlens[b] are not computed
   // (their O / L are left untouched: the caller zero-fills).
   const int* seqlens;
+  // Dropout of the attention probabilities (kDrop instantiations only; 16-bit dtypes): see fa_dropout.cuh.
+  DropParams drop;
 };
 
 // kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
@@ -78,13 +81,14 @@ struct FwdCfg {
   static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kD;
 };
 
-template <int kElt, int kD, bool kCausal>
+template <int kElt, int kD, bool kCausal, bool kDrop = false>
 __global__ void __launch_bounds__(384, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<kD, kElt>;
   constexpr bool kF8 = Cfg::kF8, kBf16 = kElt == 1, kE5M2 = kElt == 4;
   static_assert(!kF8 || kD == 128, "the FP8 forward runs at D = 128 (one 128-byte box per row); pad in the caller");
+  static_assert(!(kF8 && kDrop), "dropout is implemented for the 16-bit kernels");
   constexpr int NS = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -248,6 +252,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int my_nkv = nkv[t];
     const int q_row = q0 + 128 * t + row;             // global query index
     const float sl2 = p.scale_log2;
+    // dropout: this thread walks row q_row of the mask, one hash per pair of keys (fa_dropout.cuh)
+    uint32_t drop_row = 0, drop_shift = 0;
+    if constexpr (kDrop) {
+      drop_row = drop_key(p.drop, b * p.H + h) + drop_word_index(q_row, 0);
+      drop_shift = 16u * (q_row & 1);
+    }
 
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < my_nkv; ++j) {
@@ -329,7 +339,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             } else {
               p0 = ex2_approx(x0), p1 = ex2_approx(x1);
             }
-            ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));
+            ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));   // the row sum is that of the undropped P
+            if constexpr (kDrop) {
+              bool keep0, keep1;
+              drop_keep_pair<8>(drop_row + (uint32_t)(kv0 >> 1) + (uint32_t)(c * 16 + i), drop_shift, p.drop.thresh,
+                                keep0, keep1);
+              p0 = keep0 ? p0 : 0.f;
+              p1 = keep1 ? p1 : 0.f;
+            }
             pk[i] = pack2<kBf16>(p0, p1);
           }
           tmem_st_x16(tS + c * 16, pk);
@@ -384,7 +401,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (my_nkv > 0) {
       mbar_wait(&o_full[t], (my_nkv - 1) & 1);
       tc_fence_after();
-      const float inv_l = 1.0f / l;
+      const float inv_l = (kDrop ? p.drop.rp : 1.0f) / l;   // kept probabilities are scaled by 1 / (1 - p_drop)
       const bool in_range = q_row < nv;
       // Epilogue: O_t / l -> output dtype -> this tile's Q staging buffer (dead since its last S MMA; same size as the O
       // tile) -> global.  Going through shared memory turns "thread = row" into "warp = two full rows": every warp

@@ -13,6 +13,7 @@
 // micro-tile of the D-wide accumulators.  Rows past N are loaded as zeros and never stored.
 #pragma once
 
+#include "fa_dropout.cuh"
 #include "sm100_ptx.cuh"
 
 namespace fa {
@@ -28,6 +29,7 @@ struct SimtParams {
   float scale_log2;  // scale * log2(e)
   int causal;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; rows past it are loaded as zeros
+  DropParams drop;     // dropout of the attention probabilities (thresh = 0: off), fa_dropout.cuh
 };
 
 constexpr int kSimtTile = 64;
@@ -184,6 +186,8 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 #pragma unroll
     for (int j = 0; j < kAcc; ++j) acc[i][j] = 0.f;
   }
+  const uint32_t drop_thresh = p.drop.thresh;
+  const uint32_t dkey = drop_thresh ? drop_key(p.drop, b * p.H + h) : 0u;
   const int n_kv = p.causal ? min((nv + 63) / 64, qb + 1) : (nv + 63) / 64;
   for (int jb = 0; jb < n_kv; ++jb) {
     const int k0 = jb * 64;
@@ -214,7 +218,8 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         prv[j] = exp2f(s[i][j] - m_safe);
-        rs += prv[j];
+        rs += prv[j];   // the row sum is that of the undropped P
+        if (drop_thresh && !drop_keep(dkey, row, k0 + tx * 4 + j, drop_thresh)) prv[j] = 0.f;
       }
       rs = half16_sum(rs);
       l[i] = l[i] * alpha + rs;
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
     if (row >= nv) continue;
-    const float inv = 1.0f / l[i];
+    const float inv = (drop_thresh ? p.drop.rp : 1.0f) / l[i];
     float* orow = p.out_o + b * p.o_s[0] + h * p.o_s[1] + (int64_t)row * p.o_s[2];
 #pragma unroll
     for (int cc = 0; cc < kAcc / 4; ++cc) {
@@ -246,9 +251,10 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 
 // P and dS for one 64x64 tile from raw S = Q K^T and dP = dO V^T (shared by both backward kernels).
 // s <- P, dp <- dS (unscaled: the softmax scale is applied once to the finished dQ / dK accumulators).
+// Dropout (thresh != 0): s <- keep o P (the 1 / (1 - p) goes into the dV epilogue), dS = P o (keep * rp * dP - delta).
 __device__ __forceinline__ void simt_p_ds(float (&s)[4][4], float (&dp)[4][4], const float (&lse)[4],
                                           const float (&dl)[4], int q0, int k0, int ty, int tx, int N, int causal,
-                                          float scale_log2) {
+                                          float scale_log2, uint32_t dkey, uint32_t drop_thresh, float drop_rp) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
@@ -257,8 +263,14 @@ __device__ __forceinline__ void simt_p_ds(float (&s)[4][4], float (&dp)[4][4], c
       const int col = k0 + tx * 4 + j;
       const bool dead = (col >= N) || (row >= N) || (causal && col > row);
       const float pv = dead ? 0.f : exp2f(fmaf(s[i][j], scale_log2, -lse[i]));
-      s[i][j] = pv;
-      dp[i][j] = pv * (dp[i][j] - dl[i]);
+      if (drop_thresh) {
+        const bool keep = drop_keep(dkey, row, col, drop_thresh);
+        s[i][j] = keep ? pv : 0.f;
+        dp[i][j] = pv * ((keep ? drop_rp * dp[i][j] : 0.f) - dl[i]);
+      } else {
+        s[i][j] = pv;
+        dp[i][j] = pv * (dp[i][j] - dl[i]);
+      }
     }
   }
 }
@@ -289,6 +301,8 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
   simt_load_transposed<kD>(Kt, p.k + b * p.k_s[0] + h * p.k_s[1] + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
   simt_load_transposed<kD>(Vt, p.v + b * p.v_s[0] + h * p.v_s[1] + (int64_t)k0 * p.v_s[2], p.v_s[2], nv - k0);
 
+  const uint32_t dkey = p.drop.thresh ? drop_key(p.drop, b * p.H + h) : 0u;
+  const float dv_mul = p.drop.thresh ? p.drop.rp : 1.0f;
   float dk[4][kAcc], dv[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
       lse[i] = row < nv ? lsep[row] : 0.f;
       dl[i] = row < nv ? dlp[row] : 0.f;
     }
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       *reinterpret_cast<float4*>(Ps + (ty * 4 + i) * kSimtLdT + tx * 4) = make_float4(s[i][0], s[i][1], s[i][2], s[i][3]);
@@ -336,7 +350,8 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
             make_float4(dk[i][cc * 4 + 0] * p.scale, dk[i][cc * 4 + 1] * p.scale, dk[i][cc * 4 + 2] * p.scale,
                         dk[i][cc * 4 + 3] * p.scale);
         *reinterpret_cast<float4*>(dvrow + cc * 64 + tx * 4) =
-            make_float4(dv[i][cc * 4 + 0], dv[i][cc * 4 + 1], dv[i][cc * 4 + 2], dv[i][cc * 4 + 3]);
+            make_float4(dv[i][cc * 4 + 0] * dv_mul, dv[i][cc * 4 + 1] * dv_mul, dv[i][cc * 4 + 2] * dv_mul,
+                        dv[i][cc * 4 + 3] * dv_mul);
       }
     }
   }
@@ -366,6 +381,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
   simt_load_rowmajor<kD>(Qs, SS::kLdR, p.q + b * p.q_s[0] + h * p.q_s[1] + (int64_t)q0 * p.q_s[2], p.q_s[2], nv - q0);
   simt_load_rowmajor<kD>(dOs, SS::kLdR, p.dout + b * p.do_s[0] + h * p.do_s[1] + (int64_t)q0 * p.do_s[2], p.do_s[2],
                          nv - q0);
+  const uint32_t dkey = p.drop.thresh ? drop_key(p.drop, b * p.H + h) : 0u;
   float lse[4], dl[4], dq[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
     float s[4][4], dp[4][4];
     simt_scores_rt<kD>(s, Qs, SS::kLdR, Kt, ty, tx);
     simt_scores_rt<kD>(dp, dOs, SS::kLdR, Vt, ty, tx);
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(dSs + (ty * 4 + i) * kSimtLdT + tx * 4) =

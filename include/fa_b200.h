@@ -54,11 +54,16 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
  * this stands where a caller would otherwise follow fa_fwd by an NCCL all-gather of O along H.
  * `seqlens` (device pointer to B int32, or NULL) is a key-padding mask — "masking" on the reference's roadmap
  * (README.md:35-37): batch element b has seqlens[b] valid tokens; keys beyond are masked out, query rows beyond are not
- * computed and their O / lse are left untouched (the caller zero-fills).  All dtypes. */
+ * computed and their O / lse are left untouched (the caller zero-fills).  All dtypes.
+ * `dropout_p` in [0, 1) drops attention probabilities inside the kernel — "dropout ... fused in the kernel" on the same
+ * roadmap (README.md:35-37); float16 / bfloat16 / float32.  The probability is quantised to round(256 p) / 256 (0 = off)
+ * and kept entries are scaled by 1 / (1 - that); lse stays the logsumexp of the undropped scores.  The keep mask is a
+ * pure function of (dropout_seed, b, h, query, key), restated by the oracle (oracle/attention_oracle.py:
+ * dropout_keep_mask); fa_bwd_partial regenerates it from the same (dropout_p, dropout_seed). */
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
-                 void* const* peer_o, const int32_t* seqlens, void* stream);
+                 void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed, void* stream);
 
 /* Backward preprocess: delta[b,h,i] = sum_d O[b,h,i,d] * dO[b,h,i,d]  (fp32 accumulate).
  * Replaces bwd_D_kernel[grid](...) at flash_attention_torch.py:125-133 and flash_attention_wrappers.py:110-118. */
@@ -89,7 +94,8 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
  * rows beyond seqlens[b] are left untouched (the caller zero-fills).  The reference has a single backward launch (flash_attention_torch.py:136-154)
  * whose dQ part is the spin-locked read-modify-write of flash_attention_kernels.py:305-320; here the two parts are
  * separate kernels, exposed for callers that need only some gradients and for per-kernel timing.  Outputs not
- * selected are left untouched (their pointers must still be valid). */
+ * selected are left untouched (their pointers must still be valid).  `dropout_p`, `dropout_seed`: the values the forward
+ * ran with (two-kernel path only; `delta` must come from the dropped-out O, as fa_bwd_preprocess gives). */
 #define FA_BWD_DKDV 1
 #define FA_BWD_DQ 2
 #define FA_BWD_FUSED 4
@@ -98,7 +104,8 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
-                   int causal, int which, const int32_t* seqlens, void* stream);
+                   int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                   void* stream);
 
 /* Sequence-parallel (ring) attention helpers — no counterpart in the reference (single GPU); they sit where a caller that
  * shards the SEQUENCE across GPUs combines what fa_fwd / fa_bwd return for one key / value shard at a time.

@@ -816,3 +816,128 @@ def test_bnhd_storage_viewed_as_bhnd_needs_no_copy_and_matches():
     g2 = flash_attention_backward(tq, tk, tv, O2, tdo, L2, DEV, False, True, 0.09)
     for a, b in zip(g1, g2):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ in-kernel dropout
+def _run_dropout(Q, K, V, dO, causal, scale, p, seed, seqlens=None):
+    q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
+    O, L = flash_attention_forward(q, k, v, DEV, causal, scale, seqlens, p, seed)
+    g = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, seqlens, p, seed)
+    torch.cuda.synchronize()
+    return (O.cpu(), L.cpu()) + tuple(t.cpu() for t in g)
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float32, 128)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_dropout_mask_is_bit_exact_in_all_three_kernels(dtype, D, causal):
+    """The keep mask every kernel regenerates equals the oracle's, entry by entry.  Q = 0 makes P uniform, and
+    identity-like V / dO / K make single entries of the dropped P visible: O[i, d] = keep(i, d) P rp (forward, row walk),
+    dV[j, d] = keep(d, j) P rp (dK/dV kernel, column walk), sign(dQ[i, d]) = +/- for kept / dropped (dQ kernel)."""
+    B, H, N, p, seed = 1, 2, 256, 0.25, 987654321012345
+    keep = orc.dropout_keep_mask(seed, B, H, N, p)                      # (B,H,N,N)
+    eye = torch.eye(128)
+    Q = torch.zeros(B, H, N, D, dtype=dtype)
+    ones = torch.ones(B, H, N, D, dtype=dtype)
+    tri = torch.ones(N, N, dtype=torch.bool).tril() if causal else torch.ones(N, N, dtype=torch.bool)
+    for sel in (0, 1):
+        half = torch.zeros(N, D)
+        half[sel * 128:(sel + 1) * 128] = eye
+        half = half.to(dtype).expand(B, H, N, D).contiguous()
+        ks = slice(sel * 128, (sel + 1) * 128)
+        # forward: V = identity on keys [ks] -> O[i, d] = keep(i, ks[d]) * P(i) * rp
+        # (a causally masked entry whose exponential went through the FMA-pipe polynomial is 2^-125, not 0: "> 1e-30")
+        O = _run_dropout(Q, ones, half, ones, causal, 1.0, p, seed)[0]
+        assert torch.equal(O.float() > 1e-30, keep[..., ks] & tri[:, ks]), ("forward", sel)
+        # dK/dV kernel: dO = identity on queries [ks] -> dV[j, d] = keep(ks[d], j) * P * rp
+        dV = _run_dropout(Q, ones, ones, half, causal, 1.0, p, seed)[4]
+        assert torch.equal(dV != 0, (keep[:, :, ks, :] & tri[ks, :]).transpose(-1, -2)), ("dkdv", sel)
+        # dQ kernel: K = identity on keys [ks], V = 1, dO = 1/D -> dP = 1, delta ~ 1, dQ[i, d] = P (keep rp - delta)
+        dQ = _run_dropout(Q, half, ones, ones / D, causal, 1.0, p, seed)[2]
+        # (rows that see few keys can have every key kept, i.e. delta = rp and dS = 0: start the causal check at row 64)
+        valid = tri[:, ks].clone()
+        valid[:64 if causal else 0] = False
+        valid = valid.expand(B, H, N, 128)
+        assert torch.equal((dQ > 0)[valid], keep[..., ks][valid]), ("dq", sel)
+        assert not (dQ == 0)[valid].any() and not dQ[~tri[:, ks].expand(B, H, N, 128)].any()
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64), (torch.bfloat16, 64), (torch.float32, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("N", [384, 200])
+def test_dropout_parity(dtype, D, causal, N):
+    """O, L, dQ, dK, dV with in-kernel dropout against the float64 closed form with the oracle's mask."""
+    B, H, p, seed = 2, 3, 0.2, 20240 + N
+    scale = 1.0 / math.sqrt(D)
+    Q, K, V, dO = make_inputs(77, B, H, N, D, dtype)
+    O, L, dQ, dK, dV = _run_dropout(Q, K, V, dO, causal, scale, p, seed)
+    keep = orc.dropout_keep_mask(seed, B, H, N, p)
+    ref = orc.attention_dropout_grads_fp64(Q.float(), K.float(), V.float(), dO.float(), scale, causal, keep, p)
+    rp = 256.0 / (256.0 - orc.dropout_threshold(p))
+    o_err = (O.double() - ref["O"]).abs()
+    if dtype == torch.float32:
+        assert o_err.max().item() <= 1e-4 and (L.double() - ref["L"]).abs().max().item() <= 1e-4
+    else:
+        p_absv = orc.reference_sdpa(Q.float(), K.float(), V.float().abs(), scale, causal).double()
+        bound = rp * (2e-3 + 2.0 ** -(MANT_BITS[dtype] + 2) * p_absv) + out_half_ulp(ref["O"], dtype)
+        assert (o_err <= bound).all(), f"O err {o_err.max().item():.3e}"
+        assert (L.double() - ref["L"]).abs().max().item() <= 2e-3
+    for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        e = rel_err(got, ref[name])
+        assert e <= (2e-4 if dtype == torch.float32 else 1e-2), f"{name} rel err {e:.3e}"
+    # L is the logsumexp of the undropped scores: bitwise the same as without dropout
+    q, k, v = (t.to(DEV) for t in (Q, K, V))
+    assert torch.equal(flash_attention_forward(q, k, v, DEV, causal, scale)[1].cpu(), L)
+
+
+def test_dropout_with_key_padding_and_padded_head_size():
+    """dropout composes with seqlens (mask indexed by absolute positions) and with a head size that needs padding."""
+    B, H, N, d, p, seed = 3, 2, 300, 40, 0.3, 5150
+    lens = [300, 130, 77]
+    scale = 1.0 / math.sqrt(d)
+    Q, K, V, dO = make_inputs(78, B, H, N, d, torch.bfloat16)
+    O, L, dQ, dK, dV = _run_dropout(Q, K, V, dO, True, scale, p, seed, torch.tensor(lens, dtype=torch.int32))
+    keep = orc.dropout_keep_mask(seed, B, H, N, p)
+    for b, n in enumerate(lens):
+        r = orc.attention_dropout_grads_fp64(Q[b:b + 1, :, :n].float(), K[b:b + 1, :, :n].float(), V[b:b + 1, :, :n].float(),
+                                             dO[b:b + 1, :, :n].float(), scale, True, keep[b:b + 1, :, :n, :n], p)
+        assert (O[b:b + 1, :, :n].double() - r["O"]).abs().max() <= 3e-2   # bf16 output rounding at |O| ~ 3
+        for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+            assert rel_err(got[b:b + 1, :, :n], r[name]) <= 1e-2, (name, b)
+            assert not got[b, :, n:].float().abs().any()
+
+
+def test_dropout_autograd_seeding_and_determinism():
+    B, H, N, D = 2, 2, 512, 128
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(79, B, H, N, D, torch.bfloat16))
+
+    def run(*extra):
+        q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+        O = FlashAttention.apply(q, k, v, True, 0.09, None, *extra)
+        O.backward(dO)
+        return O.detach(), q.grad, k.grad, v.grad
+
+    a, b, c = run(0.1, 11), run(0.1, 11), run(0.1, 12)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)                       # same seed: bit-identical forward and backward
+    assert not torch.equal(a[0], c[0])                 # another seed: another mask
+    for x, y in zip(run(0.0, 11), run()):
+        assert torch.equal(x, y)                       # p = 0 is the no-dropout kernel
+    torch.manual_seed(123)
+    d1 = run(0.1)
+    torch.manual_seed(123)
+    d2 = run(0.1)
+    assert torch.equal(d1[0], d2[0]) and torch.equal(d1[1], d2[1])   # default seed follows torch.manual_seed
+    assert not torch.equal(run(0.1)[0], d1[0])                       # and advances from call to call
+    # unbiased: the mean over masks approaches the undropped output
+    base = run()[0].float()
+    acc = torch.zeros_like(base)
+    for s in range(64):
+        acc += FlashAttention.apply(Q, K, V, True, 0.09, None, 0.5, 1000 + s).float()
+    late = slice(256, None)   # rows with many keys: the mask noise averages out
+    assert (acc[:, :, late] / 64 - base[:, :, late]).abs().mean().item() < 0.03
+    with pytest.raises(TypeError):
+        _native.forward(Q.to(torch.float8_e4m3fn), K.to(torch.float8_e4m3fn), V.to(torch.float8_e4m3fn), True, 0.09,
+                        dropout_p=0.5, dropout_seed=1)
+    with pytest.raises(_lib.FlashAttentionLibraryError):
+        _native.backward(Q, K, V, a[0], dO, torch.zeros(B, H, N, device=DEV), True, 0.09, which=_native.BWD_FUSED,
+                         dropout_p=0.5, dropout_seed=1)

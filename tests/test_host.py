@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 3
+    assert lib.fa_version() == 4
     assert isinstance(lib.fa_last_error(), bytes)
 
 
@@ -156,3 +156,86 @@ def test_header_is_plain_c_and_matches_the_library(tmp_path):
     out = subprocess.run([gcc, str(tmp_path / "abi_check.o"), "-L", str(lib.parent), f"-l:{lib.name}", "-o",
                           str(tmp_path / "abi_check")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-2000:]   # every declared symbol resolves against the shared library
+
+
+def test_dropout_mask_host_compile_matches_the_oracle_bit_for_bit(tmp_path):
+    """csrc/fa_dropout.cuh compiled for the host (g++): the scalar form and both pair walks the tcgen05 kernels use
+    (row walk = forward / dQ, column walk = dK/dV) reproduce oracle.dropout_keep_mask exactly."""
+    import shutil
+    import subprocess
+
+    import numpy as np
+
+    from oracle import attention_oracle as orc
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    B, H, N, p, seed = 2, 3, 40, 0.3, 0x1234567890ABCDEF
+    src = tmp_path / "mask.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#include "fa_dropout.cuh"
+int main() {
+  const int B = %d, H = %d, N = %d;
+  fa::DropParams d{%du, %uu, %uu, 1.f};
+  for (int bh = 0; bh < B * H; ++bh) {
+    const uint32_t key = fa::drop_key(d, bh);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; j += 2) {
+        bool r0, r1, c0, c1;   // row walk from (i, j); column walk from (j, i) i.e. queries j, j+1 of key i
+        fa::drop_keep_pair<8>(key + fa::drop_word_index(i, j), 16u * (i & 1), d.thresh, r0, r1);
+        fa::drop_keep_pair<16>(key + fa::drop_word_index(j, i), 8u * (i & 1), d.thresh, c0, c1);
+        std::printf("%%d%%d%%d%%d%%d%%d\n", (int)fa::drop_keep(key, i, j, d.thresh), (int)fa::drop_keep(key, i, j + 1, d.thresh),
+                    (int)r0, (int)r1, (int)c0, (int)c1);
+      }
+  }
+  return 0;
+}
+''' % (B, H, N, orc.dropout_threshold(p), seed & 0xFFFFFFFF, seed >> 32))
+    exe = tmp_path / "mask"
+    subprocess.run([gxx, "-O1", "-std=c++17", "-I", str(_lib.CSRC), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = np.array([[int(ch) for ch in line] for line in out], dtype=bool).reshape(B * H, N, N // 2, 6)
+    keep = orc.dropout_keep_mask(seed, B, H, N, p).numpy().reshape(B * H, N, N)
+    assert (got[..., 0] == keep[:, :, 0::2]).all() and (got[..., 1] == keep[:, :, 1::2]).all()   # scalar form
+    assert (got[..., 2] == keep[:, :, 0::2]).all() and (got[..., 3] == keep[:, :, 1::2]).all()   # row walk
+    keep_t = keep.transpose(0, 2, 1)   # [key][query]
+    assert (got[..., 4] == keep_t[:, :, 0::2]).all() and (got[..., 5] == keep_t[:, :, 1::2]).all()   # column walk
+
+
+def test_dropout_mask_statistics_and_quantisation():
+    from oracle import attention_oracle as orc
+
+    assert _native.dropout_threshold(0.0) == 0 and _native.dropout_threshold(0.001) == 0
+    assert _native.dropout_threshold(0.1) == orc.dropout_threshold(0.1) == 26
+    assert _native.dropout_threshold(0.999) == 255
+    with pytest.raises(ValueError):
+        _native.dropout_threshold(1.0)
+    for p in (0.1, 0.5):
+        keep = orc.dropout_keep_mask(42, 2, 4, 512, p)
+        rate = 1.0 - orc.dropout_threshold(p) / 256.0
+        n = keep.numel()
+        assert abs(keep.double().mean().item() - rate) < 5.0 * (rate * (1 - rate) / n) ** 0.5
+        # rows, columns and heads are decorrelated: per-row keep rates scatter like independent Bernoulli draws
+        rows = keep.double().mean(-1)
+        assert abs(rows.std().item() - (rate * (1 - rate) / 512) ** 0.5) < 0.2 * (rate * (1 - rate) / 512) ** 0.5
+        assert (keep[0, 0] != keep[0, 1]).double().mean().item() > 0.5 * 2 * rate * (1 - rate)
+    assert not torch.equal(orc.dropout_keep_mask(1, 1, 1, 64, 0.5), orc.dropout_keep_mask(2, 1, 1, 64, 0.5))
+
+
+def test_c_abi_rejects_bad_dropout_arguments():
+    lib = _lib.load()
+    s = (ctypes.c_int64 * 4)(64 * 128, 128 * 64, 64, 1)
+    null = ctypes.c_void_p(0)
+    peers = (ctypes.c_void_p * 1)()
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 1.0, 0, null)
+    assert rc < 0 and b"dropout_p" in lib.fa_last_error()
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.5, 0, null)
+    assert rc < 0 and b"FP8" in lib.fa_last_error()
+    rc = lib.fa_bwd_partial(null, null, null, null, null, null, null, null, null, null, 0, 1, 1, 128, 64, s, s, s, s, s, s, s,
+                            1, 1.0, 0, 4, null, 0.5, 0, null)
+    assert rc < 0 and b"FA_BWD_FUSED" in lib.fa_last_error()
