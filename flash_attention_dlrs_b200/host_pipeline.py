@@ -3,8 +3,10 @@ pipelined against the kernels.
 
 Every (batch, head) pair is an independent problem, so the (B*H) axis is cut into chunks; chunk c+1 is copied in on
 a copy stream while chunk c runs on the compute stream and the results of chunk c-1 are copied out on a third
-stream.  PCIe is full duplex, so the step costs about max(H2D, D2H, compute) instead of their sum.  The kernels
-are the same C-ABI entry points (`_native.forward` / `_native.backward`); nothing is computed on the host.
+stream.  PCIe is full duplex, so the step costs about max(H2D, D2H, compute) instead of their sum.  Consecutive
+run() calls pipeline into each other as well: the staging buffers are guarded by events that persist across calls, so
+the first uploads of step k+1 overlap the last kernels and downloads of step k (no fill / drain bubble per step).
+The kernels are the same C-ABI entry points (`_native.forward` / `_native.backward`); nothing is computed on the host.
 """
 from __future__ import annotations
 
@@ -50,16 +52,15 @@ class HostAttentionPipeline:
 
     def run(self, host_in, host_out, causal: bool = False, softmax_scale: float = 1.0, lse_out=None):
         """host_in = (Q, K, V[, dO]) pinned (B,H,N,D) tensors; host_out = (O[, dQ, dK, dV]) pinned tensors written in
-        place.  Asynchronous with respect to the host except for stream bookkeeping; the caller synchronises (the
-        returned event is recorded after the last device->host copy)."""
+        place.  Asynchronous with respect to the host, and the calling stream does not wait for the copies either: the
+        caller synchronises on the returned event (recorded after the last device->host copy) before reading
+        `host_out` or rewriting `host_in`.  Calls must come from one stream (the staging buffers are ordered by events
+        recorded on it)."""
         compute = torch.cuda.current_stream(self.device)
         hin = [_as_bh(t) for t in host_in]
         hout = [_as_bh(t) for t in host_out]
         per, nc = self.per, self.chunks
-        for ev in self.ev_in_free + self.ev_out_free:
-            ev.record(compute)
-        self.s_in.wait_stream(compute)
-        self.s_out.wait_stream(compute)
+        # ev_in_free / ev_out_free carry over from the previous call (an event never recorded does not block)
 
         def copy_in(c):
             b = c & 1
@@ -92,7 +93,6 @@ class HostAttentionPipeline:
                 self.ev_out_free[b].record(self.s_out)
         done = torch.cuda.Event()
         done.record(self.s_out)
-        compute.wait_stream(self.s_out)
         return done
 
 

@@ -29,7 +29,11 @@ def both():
 bd = timeit(both)
 print("simultaneous H2D + D2H %.2f ms = %.1f GB/s each way" % (bd, 0.537 / bd * 1e3))
 for duplex in (False, True):
-    for chunks in (4, 8, 16):
+    for chunks in (4, 8, 16, 32):
         pipe = HostAttentionPipeline(B, H, N, D, torch.bfloat16, dev, chunks=chunks, duplex=duplex)
-        ms = timeit(lambda: pipe.run(host, out, True, D ** -0.5))
+        def steps(n=5):   # n pipelined steps; the stream waits for the last download before the closing event
+            for _ in range(n):
+                done = pipe.run(host, out, True, D ** -0.5)
+            torch.cuda.current_stream().wait_event(done)
+        ms = timeit(steps, reps=2) / 5
         print("pipeline duplex=%s chunks=%d: %.2f ms" % (duplex, chunks, ms))
