@@ -941,3 +941,53 @@ def test_dropout_autograd_seeding_and_determinism():
     with pytest.raises(_lib.FlashAttentionLibraryError):
         _native.backward(Q, K, V, a[0], dO, torch.zeros(B, H, N, device=DEV), True, 0.09, which=_native.BWD_FUSED,
                          dropout_p=0.5, dropout_seed=1)
+
+
+# ------------------------------------------------------------------------------------------------ randomized combinations
+@pytest.mark.parametrize("case", range(24))
+def test_randomized_feature_combinations(case):
+    """Seeded random draws over everything the default path takes at once — dtype, head size (padded or not), ragged N,
+    causal, scale, per-batch lengths, dropout — against the float64 closed form evaluated per batch element."""
+    rng = np.random.default_rng(1000 + case)
+    dtype = (torch.bfloat16, torch.float16, torch.float32)[case % 3]
+    d = int(rng.choice([16, 24, 40, 64, 72, 128]))
+    N = int(rng.choice([1, 17, 127, 128, 129, 255, 300, 511, 640]))
+    B, H = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    causal = bool(rng.integers(0, 2))
+    scale = float(rng.choice([1.0 / math.sqrt(d), 0.05, 0.3]))
+    p = float(rng.choice([0.0, 0.0, 0.1, 0.5]))
+    seed = int(rng.integers(0, 2 ** 62))
+    lens = [int(x) for x in rng.integers(0, N + 1, size=B)] if rng.integers(0, 2) else None
+    Q, K, V, dO = make_inputs(2000 + case, B, H, N, d, dtype)
+    sl = None if lens is None else torch.tensor(lens, dtype=torch.int32)
+    O, L, dQ, dK, dV = _run_dropout(Q, K, V, dO, causal, scale, p, seed, sl)
+    keep = orc.dropout_keep_mask(seed, B, H, N, p)
+    rp = 256.0 / (256.0 - orc.dropout_threshold(p))
+    what = f"case {case}: {dtype} d={d} N={N} B={B} H={H} causal={causal} scale={scale:.3f} p={p} lens={lens}"
+    ref = {k: torch.zeros(Q.shape, dtype=torch.float64) for k in ("O", "dQ", "dK", "dV")}
+    ref["L"] = torch.zeros(B, H, N, 1, dtype=torch.float64)
+    bound = torch.zeros(Q.shape, dtype=torch.float64)
+    for b in range(B):
+        n = N if lens is None else lens[b]
+        if n == 0:
+            continue
+        qb, kb, vb, dob = (t[b:b + 1, :, :n].float() for t in (Q, K, V, dO))
+        r = orc.attention_dropout_grads_fp64(qb, kb, vb, dob, scale, causal, keep[b:b + 1, :, :n, :n], p)
+        for k in ref:
+            ref[k][b:b + 1, :, :n] = r[k]
+        if dtype != torch.float32:
+            p_absv = orc.reference_sdpa(qb, kb, vb.abs(), scale, causal).double()
+            bound[b:b + 1, :, :n] = rp * (2e-3 + 2.0 ** -(MANT_BITS[dtype] + 2) * p_absv) + out_half_ulp(r["O"], dtype)
+        else:
+            bound[b:b + 1, :, :n] = 1e-4 * rp
+    assert ((O.double() - ref["O"]).abs() <= bound).all(), what + f" O err {(O.double() - ref['O']).abs().max():.3e}"
+    assert (L.double() - ref["L"]).abs().max() <= (1e-4 if dtype == torch.float32 else 2e-3), what
+    for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        if ref[name].abs().max() < 1e-9:
+            # one visible key per row: dS = P o (dP - delta) is identically zero in exact arithmetic, what the kernels
+            # return is the rounding of O inside delta -> absolute check
+            e = (got.double() - ref[name]).abs().max().item()
+            assert e <= (1e-4 if dtype == torch.float32 else 2e-2), what + f" {name} abs err {e:.3e} (zero reference)"
+            continue
+        e = rel_err(got, ref[name])
+        assert e <= (3e-4 if dtype == torch.float32 else 1e-2), what + f" {name} rel err {e:.3e}"
