@@ -97,7 +97,7 @@ def _declare(lib):
     lib.fa_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, vp]
     lib.fa_fwd_peers.restype = i
     lib.fa_fwd_peers.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, i, ctypes.POINTER(vp), vp,
-                                 f, ctypes.c_uint64, vp]
+                                 f, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_int64), vp]
     lib.fa_bwd_preprocess.restype = i
     lib.fa_bwd_preprocess.argtypes = [vp, vp, vp, i, i, i, i, st, st, i, vp]
     lib.fa_bwd_workspace_bytes.restype = sz
@@ -106,7 +106,8 @@ def _declare(lib):
     lib.fa_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i, vp]
     lib.fa_bwd_partial.restype = i
     lib.fa_bwd_partial.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i,
-                                   i, vp, f, ctypes.c_uint64, vp]
+                                   i, vp, f, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_int64), vp,
+                                   ctypes.POINTER(ctypes.c_int64), vp]
 
 
 def _declare_ring(lib):

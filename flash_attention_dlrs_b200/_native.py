@@ -119,8 +119,56 @@ def _dropout_args(dropout_p, dropout_seed):
     return p, int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
 
 
+class AttentionMask:
+    """An arbitrary attention mask in the layout the kernels read (include/fa_b200.h, `attn_mask`): one byte per
+    (query, key), non-zero = attend, row pitch rounded up to 128 bytes — once as [.., query, key] (forward, dQ kernel)
+    and once transposed [.., key, query] (dK/dV kernel).  Build it once and pass it as `attn_mask` to reuse the packed
+    copies across calls; a plain bool tensor is wrapped on the fly.
+
+    `mask`: bool (or any dtype, non-zero = attend) of shape (N, N), (B|1, N, N) or (B|1, H|1, N, N)."""
+
+    def __init__(self, mask: torch.Tensor):
+        if mask.dim() == 2:
+            mask = mask[None, None]
+        elif mask.dim() == 3:
+            mask = mask[:, None]
+        if mask.dim() != 4 or mask.shape[-1] != mask.shape[-2]:
+            raise ValueError(f"attn_mask must be (N, N), (B, N, N) or (B, H, N, N), got {tuple(mask.shape)}")
+        m = mask if mask.dtype == torch.bool else (mask != 0)
+        Bm, Hm, N, _ = m.shape
+        pitch = (N + 127) // 128 * 128
+
+        def pack(x):
+            buf = torch.zeros((Bm, Hm, N, pitch), dtype=torch.uint8, device=x.device)
+            buf[..., :N] = x
+            return buf
+
+        self.rows, self.cols = pack(m), pack(m.transpose(-1, -2))
+        self.shape = (Bm, Hm, N)
+
+    def args(self, B: int, H: int, N: int, device):
+        """(rows ptr, rows strides, cols ptr, cols strides) for a (B, H, N, .) problem; size-1 dims broadcast."""
+        Bm, Hm, Nm = self.shape
+        if Nm != N or Bm not in (1, B) or Hm not in (1, H):
+            raise ValueError(f"attn_mask of shape {(Bm, Hm, Nm, Nm)} does not broadcast to {(B, H, N, N)}")
+        if self.rows.device != device:
+            raise ValueError(f"attn_mask is on {self.rows.device}, the inputs on {device}")
+        out = []
+        for t in (self.rows, self.cols):
+            sB, sH, sN, _ = t.stride()
+            out += [_ptr(t), (ctypes.c_int64 * 3)(0 if Bm == 1 else sB, 0 if Hm == 1 else sH, sN)]
+        return out
+
+
+def _mask_arg(attn_mask, B, H, N, device):
+    if attn_mask is None:
+        return None, [ctypes.c_void_p(0), None, ctypes.c_void_p(0), None]
+    am = attn_mask if isinstance(attn_mask, AttentionMask) else AttentionMask(attn_mask)
+    return am, am.args(B, H, N, device)
+
+
 def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float, out=None,
-            peer_ptrs=(), seqlens=None, dropout_p: float = 0.0, dropout_seed=None):
+            peer_ptrs=(), seqlens=None, dropout_p: float = 0.0, dropout_seed=None, attn_mask=None):
     """O (B,H,N,d) in the input dtype and L (B,H,N) float32 in log2 units.  Inputs already validated.
 
     `out` = (data_ptr, element strides (sB, sH, sN, 1)) makes the kernel write O at a caller-owned address (a window of
@@ -133,13 +181,19 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
 
     `dropout_p`, `dropout_seed`: in-kernel dropout of the attention probabilities (16-bit and float32; quantised to
     dropout_threshold(p) / 256, kept entries scaled by the reciprocal of the keep rate).  The mask is a pure function
-    of (seed, b, h, query, key) — oracle/attention_oracle.py restates it; L is that of the undropped scores."""
+    of (seed, b, h, query, key) — oracle/attention_oracle.py restates it; L is that of the undropped scores.
+
+    `attn_mask`: arbitrary mask, bool (N, N) / (B|1, N, N) / (B|1, H|1, N, N) or an AttentionMask, True = attend, ANDed
+    with `causal` and `seqlens`; a query with no visible key gets O = 0, L = -inf.  16-bit and float32."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
     drop_p, drop_seed = _dropout_args(dropout_p, dropout_seed)
     if drop_p and Q.dtype in FP8_DTYPES:
         raise TypeError(f"dropout is not implemented for the FP8 forward ({Q.dtype})")
+    if attn_mask is not None and Q.dtype in FP8_DTYPES:
+        raise TypeError(f"attention masks are not implemented for the FP8 forward ({Q.dtype})")
+    am, am_args = _mask_arg(attn_mask, B, H, N, Q.device)
     if Q.numel() == 0 and out is None:   # empty batch / no heads / no tokens: nothing to launch
         return torch.empty_like(Q), torch.empty((B, H, N), dtype=torch.float32, device=Q.device)
     d_run = padded_head_dim(d, Q.dtype)
@@ -161,7 +215,7 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
         rc = lib.fa_fwd_peers(_ptr(q), _ptr(k), _ptr(v), o_ptr, _ptr(L), B, H, N, d_run,
                               _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), o_strides,
                               code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers, sl_ptr,
-                              drop_p, drop_seed, _stream_ptr(Q.device))
+                              drop_p, drop_seed, am_args[0], am_args[1], _stream_ptr(Q.device))
     _lib.check(rc, "fa_fwd")
     if O is None:
         return None, L
@@ -186,17 +240,18 @@ BWD_DKDV, BWD_DQ, BWD_FUSED = 1, 2, 4
 
 
 def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int | None = None, delta=None,
-             seqlens=None, dropout_p: float = 0.0, dropout_seed=None):
+             seqlens=None, dropout_p: float = 0.0, dropout_seed=None, attn_mask=None):
     """dQ, dK, dV (B,H,N,d) in the input dtype; deterministic (bit-identical across runs).
     `which` = None runs what fa_bwd runs: the two-kernel path (BWD_DKDV | BWD_DQ; either half can be selected alone,
     unselected outputs are uninitialised).  BWD_FUSED selects the single-pass kernel with the ordered dQ reduction
     (16-bit inputs only).  `delta` may carry a precomputed rowsum(O * dO) to skip the preprocess launch.
     `seqlens` as in forward(): gradient rows beyond seqlens[b] are zero (two-kernel path only).
-    `dropout_p`, `dropout_seed`: the values the forward ran with (two-kernel path only)."""
+    `dropout_p`, `dropout_seed`, `attn_mask`: the values the forward ran with (two-kernel path only)."""
     lib = _lib.load()
     B, H, N, d = Q.shape
     code = dtype_code(Q.dtype)
     drop_p, drop_seed = _dropout_args(dropout_p, dropout_seed)
+    am, am_args = _mask_arg(attn_mask, B, H, N, Q.device)
     if Q.dtype in FP8_DTYPES:
         raise TypeError(f"dtype {Q.dtype} not supported in backward (the FP8 path is forward-only).")
     if Q.numel() == 0:
@@ -221,7 +276,7 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
                                 d_run, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),
                                 _lib.strides4(dQ), _lib.strides4(dK), _lib.strides4(dV),
                                 code, float(softmax_scale), int(bool(causal)), int(which), sl_ptr,
-                                drop_p, drop_seed, _stream_ptr(Q.device))
+                                drop_p, drop_seed, *am_args, _stream_ptr(Q.device))
     _lib.check(rc, "fa_bwd")
     if d_run != d:
         dQ, dK, dV = dQ[..., :d], dK[..., :d], dV[..., :d]

@@ -78,19 +78,34 @@ int make_drop(const char* fn, float dropout_p, uint64_t seed, fa::DropParams* d)
   return 0;
 }
 
+// attention mask: bytes [.., row, col], non-zero = attend; strides {sB, sH, sRow} in bytes (sB / sH may be 0 = broadcast)
+int check_amask(const char* fn, const char* name, const uint8_t* m, const int64_t s[3], int N) {
+  if (!m) return 0;
+  if (!s) return fail(-14, "%s: %s given without strides", fn, name);
+  const int64_t pitch = ((int64_t)N + 127) / 128 * 128;
+  if ((reinterpret_cast<uintptr_t>(m) & 15u) != 0) return fail(-14, "%s: %s must be 16-byte aligned", fn, name);
+  if (s[2] < pitch || s[2] % 16 != 0)
+    return fail(-14, "%s: %s row pitch must be a multiple of 16 bytes and >= N rounded up to 128 (%lld), got %lld", fn, name,
+                (long long)pitch, (long long)s[2]);
+  if (s[0] < 0 || s[1] < 0 || s[0] % 16 != 0 || s[1] % 16 != 0)
+    return fail(-14, "%s: %s batch / head strides must be non-negative multiples of 16 bytes (0 = broadcast)", fn, name);
+  return 0;
+}
+
 void fill3(int64_t (&dst)[3], const int64_t s[4]) {
   dst[0] = s[0], dst[1] = s[1], dst[2] = s[2];
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <int kElt, int kD, bool kCausal, bool kDrop = false>
+template <int kElt, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 int launch_fwd16(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p, int H,
                  int B, cudaStream_t st) {
   using Cfg = fa::FwdCfg<kD, kElt>;
-  if constexpr (kElt < 3 && !kDrop) {
-    if (p.drop.thresh) return launch_fwd16<kElt, kD, kCausal, true>(tq, tk, tv, p, H, B, st);
+  if constexpr (kElt < 3 && !kDrop && !kAmask) {
+    if (p.drop.thresh) return launch_fwd16<kElt, kD, kCausal, true, false>(tq, tk, tv, p, H, B, st);
+    if (p.amask) return launch_fwd16<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
   }
-  auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal, kDrop>;
+  auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal, kDrop, kAmask>;
   if (int r = set_smem(kern, Cfg::kSmemBytes)) return r;
   dim3 grid(p.q_blocks, H, B);
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
@@ -133,13 +148,14 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------- backward (16-bit)
-template <bool kBf16, int kD, bool kCausal, bool kDrop = false>
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaStream_t st) {
-  if constexpr (!kDrop) {
-    if (p.drop.thresh) return launch_bwd16<kBf16, kD, kCausal, true>(m, p, which, st);
+  if constexpr (!kDrop && !kAmask) {
+    if (p.drop.thresh) return launch_bwd16<kBf16, kD, kCausal, true, false>(m, p, which, st);
+    if (p.amask) return launch_bwd16<kBf16, kD, kCausal, false, true>(m, p, which, st);
   }
   if (which & FA_BWD_DKDV) {
-    auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal, kDrop>;
+    auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
     if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDkdv)) return r;
     dim3 grid((p.N + 127) / 128, p.H, p.B);
     kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDkdv, st>>>(m.q, m.k, m.v, m.dout, p);
@@ -147,7 +163,7 @@ int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaSt
     if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(dK/dV) launch");
   }
   if (which & FA_BWD_DQ) {
-    auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal, kDrop>;
+    auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
     if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDq)) return r;
     dim3 grid((p.N + 127) / 128, p.H, p.B);
     kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDq, st>>>(m.q, m.k, m.v, m.dout, p);
@@ -212,7 +228,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 4; }
+int fa_version(void) { return 5; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -220,18 +236,24 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
   return fa_fwd_peers(q, k, v, o, lse, B, H, N, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale,
-                      causal, 0, nullptr, nullptr, 0.f, 0, stream);
+                      causal, 0, nullptr, nullptr, 0.f, 0, nullptr, nullptr, stream);
 }
 
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
-                 void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed, void* stream) {
+                 void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                 const uint8_t* attn_mask, const int64_t attn_mask_strides[3], void* stream) {
   g_err[0] = 0;
+  if (int r = check_amask("fa_fwd_peers", "attn_mask", attn_mask, attn_mask_strides, N)) return r;
+  if (attn_mask && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
+    return fail(-14, "fa_fwd_peers: attention masks are not implemented for the FP8 forward");
   fa::DropParams drop;
   if (int r = make_drop("fa_fwd_peers", dropout_p, dropout_seed, &drop)) return r;
   if (drop.thresh && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
     return fail(-13, "fa_fwd_peers: dropout is not implemented for the FP8 forward");
+  if (drop.thresh && attn_mask && dtype != FA_DTYPE_F32)
+    return fail(-14, "fa_fwd_peers: dropout together with an attention mask is implemented for float32 only");
   if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_o)) return fail(-12, "fa_fwd_peers: 0 <= n_peers <= 7 and peer_o non-null");
   if (n_peers > 0 && dtype == FA_DTYPE_F32) return fail(-12, "fa_fwd_peers: peer copies are implemented for the 16-bit and FP8 kernels");
   for (int i = 0; i < n_peers; ++i)
@@ -254,6 +276,8 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
     p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
     p.seqlens = seqlens;
     p.drop = drop;
+    p.amask = attn_mask;
+    if (attn_mask) p.am_s[0] = attn_mask_strides[0], p.am_s[1] = attn_mask_strides[1], p.am_s[2] = attn_mask_strides[2];
     switch (D) {
       case 16: return launch_fwd32<16>(p, st);
       case 32: return launch_fwd32<32>(p, st);
@@ -281,6 +305,8 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   for (int i = 0; i < n_peers; ++i) p.o_peer[i] = peer_o[i];
   p.seqlens = seqlens;
   p.drop = drop;
+  p.amask = attn_mask;
+  if (attn_mask) p.am_sB = attn_mask_strides[0], p.am_sH = attn_mask_strides[1], p.am_sN = attn_mask_strides[2];
 #define FA_FWD_CASE(E, DD, C) \
   if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
   FA_FWD_CASE(FA_DTYPE_BF16, 128, true)
@@ -348,7 +374,7 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
   // the single-pass kernel, whose dQ reduction is bound by the SM -> L2 path.
   return fa_bwd_partial(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, D, q_strides,
                         k_strides, v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale,
-                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, 0.f, 0, stream);
+                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, 0.f, 0, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
@@ -357,12 +383,22 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
-                   void* stream) {
+                   const uint8_t* attn_mask, const int64_t attn_mask_strides[3], const uint8_t* attn_mask_t,
+                   const int64_t attn_mask_t_strides[3], void* stream) {
   g_err[0] = 0;
+  if (int r = check_amask("fa_bwd_partial", "attn_mask", attn_mask, attn_mask_strides, N)) return r;
+  if (int r = check_amask("fa_bwd_partial", "attn_mask_t", attn_mask_t, attn_mask_t_strides, N)) return r;
+  if (attn_mask && which == FA_BWD_FUSED)
+    return fail(-14, "fa_bwd_partial: FA_BWD_FUSED takes no attention mask; use the two-kernel path");
+  if (attn_mask && !attn_mask_t && dtype != FA_DTYPE_F32)
+    return fail(-14, "fa_bwd_partial: the 16-bit kernels need the transposed mask (attn_mask_t) as well");
+  if ((bool)attn_mask_t && !attn_mask) return fail(-14, "fa_bwd_partial: attn_mask_t given without attn_mask");
   fa::DropParams drop;
   if (int r = make_drop("fa_bwd_partial", dropout_p, dropout_seed, &drop)) return r;
   if (drop.thresh && which == FA_BWD_FUSED)
     return fail(-13, "fa_bwd_partial: FA_BWD_FUSED has no dropout; use the two-kernel path");
+  if (drop.thresh && attn_mask && dtype != FA_DTYPE_F32)
+    return fail(-14, "fa_bwd_partial: dropout together with an attention mask is implemented for float32 only");
   if (which != FA_BWD_FUSED && ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ))))
     return fail(-10, "fa_bwd_partial: which must be FA_BWD_FUSED or a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
   if (which == FA_BWD_FUSED) {
@@ -399,6 +435,8 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
     p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e, p.causal = causal ? 1 : 0;
     p.seqlens = seqlens;
     p.drop = drop;
+    p.amask = attn_mask;
+    if (attn_mask) p.am_s[0] = attn_mask_strides[0], p.am_s[1] = attn_mask_strides[1], p.am_s[2] = attn_mask_strides[2];
     switch (D) {
       case 16: return launch_bwd32<16>(p, which, st);
       case 32: return launch_bwd32<32>(p, which, st);
@@ -424,6 +462,10 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e;
   p.seqlens = seqlens;
   p.drop = drop;
+  p.amask = attn_mask, p.amask_t = attn_mask_t;
+  if (attn_mask) {
+    for (int i = 0; i < 3; ++i) p.am_s[i] = attn_mask_strides[i], p.amt_s[i] = attn_mask_t_strides[i];
+  }
 #define FA_BWD_CASE(BF, DD, C)                                                                  \
   if (bf == BF && D == DD && (causal != 0) == C)                                                \
     return which == FA_BWD_FUSED ? launch_bwd16_fused<BF, DD, C>(m, p, workspace, st)           \

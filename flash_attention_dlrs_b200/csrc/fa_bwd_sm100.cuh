@@ -47,7 +47,24 @@ struct BwdParams {
   float scale, scale_log2;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; see FwdParams::seqlens
   DropParams drop;     // dropout of the attention probabilities (kDrop instantiations only), fa_dropout.cuh
+  // Arbitrary attention mask (kAmask instantiations only), bytes, non-zero = attend; see FwdParams::amask.  The dQ kernel
+  // walks query rows of `amask` [.., query, key]; the dK/dV kernel walks key rows of `amask_t` [.., key, query], the same
+  // mask transposed (made once by the caller), so both read 64 contiguous bytes per thread and half block.
+  const uint8_t *amask, *amask_t;
+  int64_t am_s[3], amt_s[3];  // {sB, sH, sRow} in bytes
 };
+
+// byte e (0..63) of a thread's 64 mask bytes held as 16 words
+__device__ __forceinline__ bool amask_byte(const uint32_t (&mk)[16], int e) {
+  return (mk[e >> 2] & (0xffu << (8 * (e & 3)))) != 0u;
+}
+__device__ __forceinline__ void amask_load64(uint32_t (&mk)[16], const uint8_t* src) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    mk[4 * i] = v.x, mk[4 * i + 1] = v.y, mk[4 * i + 2] = v.z, mk[4 * i + 3] = v.w;
+  }
+}
 
 template <int kD>
 struct BwdCfg {
@@ -98,11 +115,12 @@ __device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float 
 // kDrop: dropout — the stored P is keep o P (its 1 / (1 - p) goes into the dV epilogue) and dS = P o (keep * rp * dP - delta);
 // `drop_word` = key + word index of this thread's first element pair, `drop_shift` / kDropSecond as in fa_dropout.cuh,
 // consecutive pairs are kDropStep words apart.
-template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP, bool kDrop = false>
+// kAmask: `mk` = this thread's 64 attention-mask bytes for the half block (non-zero = attend).
+template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP, bool kDrop = false, bool kAmask = false>
 __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
                                                      uint64_t nd_c, float sl2, int row, int col0,
-                                                     uint32_t drop_word = 0, uint32_t drop_shift = 0,
-                                                     uint32_t drop_thresh = 0, float drop_rp = 1.f) {
+                                                     uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
+                                                     float drop_rp, const uint32_t (&mk)[16]) {
   constexpr uint32_t kDropStep = kTransposed ? (1u << 15) : 1u;
   constexpr int kDropSecond = kTransposed ? 16 : 8;
 #if FA_ABLATE == 3
@@ -148,6 +166,10 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
           if (kTransposed ? (row > c0) : (c0 > row)) p0 = 0.f;
           if (kTransposed ? (row > c0 + 1) : (c0 + 1 > row)) p1 = 0.f;
         }
+        if constexpr (kAmask) {
+          if (!amask_byte(mk, e)) p0 = 0.f;
+          if (!amask_byte(mk, e + 1)) p1 = 0.f;
+        }
         float d0, d1;
         if constexpr (kDrop) {
           bool keep0, keep1;
@@ -174,11 +196,11 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
 // dQ kernel flavour: per-thread statistics, dS only.  The two score accumulators are copied to registers first and
 // released to the MMA warp (`sc_free`) before any arithmetic, so the next block's score MMAs overlap this stage.
 // Output: 64 values of this thread's row as 32 packed 16-bit pairs in `pd`.
-template <bool kBf16, bool kMask, bool kDrop = false>
+template <bool kBf16, bool kMask, bool kDrop = false, bool kAmask = false>
 __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
                                                     uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32],
-                                                    uint32_t drop_word = 0, uint32_t drop_shift = 0,
-                                                    uint32_t drop_thresh = 0, float drop_rp = 1.f) {
+                                                    uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
+                                                    float drop_rp, const uint32_t (&mk)[16]) {
   uint32_t sr[64], dr[64];
   tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
   tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
@@ -213,6 +235,10 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
       if (c0 > row) p0 = 0.f;
       if (c0 + 1 > row) p1 = 0.f;
     }
+    if constexpr (kAmask) {
+      if (!amask_byte(mk, e)) p0 = 0.f;
+      if (!amask_byte(mk, e + 1)) p1 = 0.f;
+    }
     float d0, d1;
     if constexpr (kDrop) {   // dS = P o (keep * rp * dP - delta); row walk, one word per key pair
       bool keep0, keep1;
@@ -227,7 +253,7 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
 }
 
 // ================================================================================================ dK / dV
-template <bool kBf16, int kD, bool kCausal, bool kDrop = false>
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 __global__ void __launch_bounds__(384, 1)
 fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -315,7 +341,9 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int e = 0; e < 4; ++e) {
         const int r = lane * 4 + e;
         const bool ok = q0 + r < nv;
-        st[r] = ok ? -lsep[q0 + r] : -INFINITY;  // rows past the valid length: P = exp2(-inf) = 0
+        float nl = ok ? -lsep[q0 + r] : -INFINITY;  // rows past the valid length: P = exp2(-inf) = 0
+        if (kAmask && nl == INFINITY) nl = -INFINITY;   // a query that saw no key (L = -inf): P = 0 as well
+        st[r] = nl;
         st[128 + r] = ok ? -dlp[q0 + r] : 0.f;
       }
       mbar_arrive(&stat_full[s]);
@@ -405,19 +433,25 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       drop_shift = 8u * ((k0 + row) & 1);
     }
 
+    const uint8_t* amt_row = nullptr;   // this key's row of the transposed attention mask
+    if constexpr (kAmask)
+      amt_row = p.amask_t + (int64_t)b * p.amt_s[0] + (int64_t)h * p.amt_s[1] + (int64_t)min(k0 + row, p.N - 1) * p.amt_s[2];
+
     for (int it = 0; it < n_it; ++it) {
       const int s = it % NS;
+      uint32_t mk[16] = {};
+      if constexpr (kAmask) amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64);
       mbar_wait(&stat_full[s], (it / NS) & 1);
       mbar_wait(&sc_full[half], it & 1);
       tc_fence_after();
       const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
       if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
-        bwd_elementwise_half<kBf16, true, true, true, true, kDrop>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
-                                                                   drop_shift, p.drop.thresh, p.drop.rp);
+        bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
+                                                                           drop_shift, p.drop.thresh, p.drop.rp, mk);
       else
-        bwd_elementwise_half<kBf16, true, false, true, true, kDrop>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
-                                                                    drop_shift, p.drop.thresh, p.drop.rp);
+        bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64,
+                                                                            dw, drop_shift, p.drop.thresh, p.drop.rp, mk);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[half]);
@@ -443,7 +477,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ================================================================================================ dQ
-template <bool kBf16, int kD, bool kCausal, bool kDrop = false>
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 __global__ void __launch_bounds__(384, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -624,7 +658,11 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q_row = q0 + row;
     const bool in_range = q_row < nv;
     const int64_t stat_idx = ((int64_t)b * p.H + h) * p.N + q_row;
-    const float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
+    float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
+    if (kAmask && neg_lse == INFINITY) neg_lse = -INFINITY;   // a query that saw no key (L = -inf): P = 0
+    const uint8_t* am_row = nullptr;   // this query's row of the attention mask
+    if constexpr (kAmask)
+      am_row = p.amask + (int64_t)b * p.am_s[0] + (int64_t)h * p.am_s[1] + (int64_t)min(q_row, p.N - 1) * p.am_s[2];
     const float neg_dl = in_range ? -p.delta[stat_idx] : 0.f;
     const uint64_t nl2 = f32x2_pack(neg_lse, neg_lse), nd2 = f32x2_pack(neg_dl, neg_dl);
     // dropout: this thread walks row q_row of the mask, one hash per pair of keys (fa_dropout.cuh)
@@ -661,20 +699,22 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t sds = smem_u32(half == 0 ? sQ : sDO);   // this half's dS box (see the MMA warp)
     for (int it = 0; it < n_it; ++it) {
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 0);   // about to wait for scores
+      uint32_t mk[16] = {};
+      if constexpr (kAmask) amask_load64(mk, am_row + it * 128 + half * 64);
       mbar_wait(&sc_full[half], it & 1);
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();
       uint32_t pd[32];
       const uint32_t dw = drop_row + (uint32_t)(it * 64);
       if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
-        dq_elementwise_half<kBf16, true, kDrop>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw, drop_shift,
-                                                p.drop.thresh, p.drop.rp);
+        dq_elementwise_half<kBf16, true, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
+                                                        drop_shift, p.drop.thresh, p.drop.rp, mk);
       else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
-        dq_elementwise_half<kBf16, true, kDrop>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1, half * 64, pd,
-                                                dw, drop_shift, p.drop.thresh, p.drop.rp);
+        dq_elementwise_half<kBf16, true, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
+                                                        half * 64, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mk);
       else
-        dq_elementwise_half<kBf16, false, kDrop>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
-                                                 drop_shift, p.drop.thresh, p.drop.rp);
+        dq_elementwise_half<kBf16, false, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
+                                                         drop_shift, p.drop.thresh, p.drop.rp, mk);
       if (it > 0) mbar_wait(&ds_free[half], (it - 1) & 1);        // dQ MMAs of the previous block have read the box
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)

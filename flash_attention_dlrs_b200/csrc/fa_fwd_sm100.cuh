@@ -58,6 +58,12 @@ struct FwdParams {
   const int* seqlens;
   // Dropout of the attention probabilities (kDrop instantiations only; 16-bit dtypes): see fa_dropout.cuh.
   DropParams drop;
+  // Arbitrary attention mask (kAmask instantiations only; 16-bit dtypes): one byte per (query, key), non-zero = attend,
+  // combined (AND) with the causal flag and seqlens.  Row pitch am_sN is a multiple of 128 bytes >= N rounded up to 128
+  // (so 16-byte loads of a key block stay inside the row); am_sB / am_sH may be 0 (broadcast).  A row with no visible
+  // key gives O = 0, L = -inf.
+  const uint8_t* amask;
+  int64_t am_sB, am_sH, am_sN;
 };
 
 // kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
@@ -81,14 +87,15 @@ struct FwdCfg {
   static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kD;
 };
 
-template <int kElt, int kD, bool kCausal, bool kDrop = false>
+template <int kElt, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 __global__ void __launch_bounds__(384, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<kD, kElt>;
   constexpr bool kF8 = Cfg::kF8, kBf16 = kElt == 1, kE5M2 = kElt == 4;
   static_assert(!kF8 || kD == 128, "the FP8 forward runs at D = 128 (one 128-byte box per row); pad in the caller");
-  static_assert(!(kF8 && kDrop), "dropout is implemented for the 16-bit kernels");
+  static_assert(!(kF8 && (kDrop || kAmask)), "dropout and attention masks are implemented for the 16-bit kernels");
+  static_assert(!(kDrop && kAmask), "dropout and an attention mask are separate instantiations");
   constexpr int NS = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,8 +266,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       drop_shift = 16u * (q_row & 1);
     }
 
+    const uint8_t* am_row = nullptr;
+    if constexpr (kAmask)
+      am_row = p.amask + (int64_t)b * p.am_sB + (int64_t)h * p.am_sH + (int64_t)min(q_row, p.N - 1) * p.am_sN;
+
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < my_nkv; ++j) {
+      uint4 mk[kAmask ? 8 : 1];   // this row's 128 mask bytes of key block j, requested before the wait for S
+      if constexpr (kAmask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
+      }
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
 #if FA_ABLATE == 3
@@ -285,6 +301,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int c = 0; c < 128; ++c)
           if (c >= limit) sr[c] = 0xff800000u;         // -inf
+      }
+      if constexpr (kAmask) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) {
+          const uint4& q4 = mk[c >> 4];
+          const uint32_t w = ((c >> 2) & 3) == 0 ? q4.x : ((c >> 2) & 3) == 1 ? q4.y : ((c >> 2) & 3) == 2 ? q4.z : q4.w;
+          if (!(w & (0xffu << (8 * (c & 3))))) sr[c] = 0xff800000u;   // -inf
+        }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -317,7 +341,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
         }
       }
-      const float neg_ms = -m_used * sl2;
+      // (with an attention mask a row may have seen no key yet: m = -inf; use 0 so that exp2(-inf - 0) = 0, not NaN)
+      const float neg_ms = (kAmask && m_used == -INFINITY) ? 0.f : -m_used * sl2;
       const uint64_t sl2_2 = f32x2_pack(sl2, sl2), nm2 = f32x2_pack(neg_ms, neg_ms);
       uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};   // four packed partial row sums (8 fp32 chains)
       if constexpr (!kF8) {
@@ -334,7 +359,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             float x0, x1;
             f32x2_unpack(x2, x0, x1);
             float p0, p1;
-            if (((kD == 64 ? FA_FWD_POLY_MASK_D64 : FA_FWD_POLY_MASK_D128) >> (i & 7)) & 1) {   // FMA-pipe exp2
+            // (the polynomial clamps at 2^-125 instead of 0: masked-out rows must sum to exactly 0, so kAmask keeps MUFU)
+            if (!kAmask && (((kD == 64 ? FA_FWD_POLY_MASK_D64 : FA_FWD_POLY_MASK_D128) >> (i & 7)) & 1)) {   // FMA-pipe exp2
               ex2_poly_x2(x0, x1, p0, p1);
             } else {
               p0 = ex2_approx(x0), p1 = ex2_approx(x1);
@@ -401,7 +427,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (my_nkv > 0) {
       mbar_wait(&o_full[t], (my_nkv - 1) & 1);
       tc_fence_after();
-      const float inv_l = (kDrop ? p.drop.rp : 1.0f) / l;   // kept probabilities are scaled by 1 / (1 - p_drop)
+      float inv_l = (kDrop ? p.drop.rp : 1.0f) / l;   // kept probabilities are scaled by 1 / (1 - p_drop)
+      if (kAmask && !(l > 0.f)) inv_l = 0.f;          // no visible key: O = 0 (and L = -inf below)
       const bool in_range = q_row < nv;
       // Epilogue: O_t / l -> output dtype -> this tile's Q staging buffer (dead since its last S MMA; same size as the O
       // tile) -> global.  Going through shared memory turns "thread = row" into "warp = two full rows": every warp

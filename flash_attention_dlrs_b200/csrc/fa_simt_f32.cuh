@@ -30,7 +30,14 @@ struct SimtParams {
   int causal;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; rows past it are loaded as zeros
   DropParams drop;     // dropout of the attention probabilities (thresh = 0: off), fa_dropout.cuh
+  // arbitrary attention mask, bytes [.., query, key], non-zero = attend (nullptr: none); strides in bytes, sB / sH may be 0
+  const uint8_t* amask;
+  int64_t am_s[3];
 };
+
+__device__ __forceinline__ bool simt_visible(const uint8_t* am_bh, int64_t am_sN, int row, int col) {
+  return am_bh == nullptr || __ldg(am_bh + (int64_t)row * am_sN + col) != 0;
+}
 
 constexpr int kSimtTile = 64;
 // columns of a D-wide accumulator one thread owns: 4 per 64-wide column group it participates in
@@ -188,6 +195,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
   }
   const uint32_t drop_thresh = p.drop.thresh;
   const uint32_t dkey = drop_thresh ? drop_key(p.drop, b * p.H + h) : 0u;
+  const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
   const int n_kv = p.causal ? min((nv + 63) / 64, qb + 1) : (nv + 63) / 64;
   for (int jb = 0; jb < n_kv; ++jb) {
     const int k0 = jb * 64;
@@ -204,7 +212,8 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = k0 + tx * 4 + j;
-        const bool dead = (col >= nv) || (p.causal && col > row);
+        const bool dead = (col >= nv) || (p.causal && col > row) ||
+                          (row < nv && !simt_visible(am_bh, p.am_s[2], row, col));
         s[i][j] = dead ? -INFINITY : s[i][j] * p.scale_log2;
         mx = fmaxf(mx, s[i][j]);
       }
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
     if (row >= nv) continue;
-    const float inv = (drop_thresh ? p.drop.rp : 1.0f) / l[i];
+    const float inv = l[i] > 0.f ? (drop_thresh ? p.drop.rp : 1.0f) / l[i] : 0.f;   // no visible key (mask): O = 0, L = -inf
     float* orow = p.out_o + b * p.o_s[0] + h * p.o_s[1] + (int64_t)row * p.o_s[2];
 #pragma unroll
     for (int cc = 0; cc < kAcc / 4; ++cc) {
@@ -254,14 +263,16 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 // Dropout (thresh != 0): s <- keep o P (the 1 / (1 - p) goes into the dV epilogue), dS = P o (keep * rp * dP - delta).
 __device__ __forceinline__ void simt_p_ds(float (&s)[4][4], float (&dp)[4][4], const float (&lse)[4],
                                           const float (&dl)[4], int q0, int k0, int ty, int tx, int N, int causal,
-                                          float scale_log2, uint32_t dkey, uint32_t drop_thresh, float drop_rp) {
+                                          float scale_log2, uint32_t dkey, uint32_t drop_thresh, float drop_rp,
+                                          const uint8_t* am_bh, int64_t am_sN) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = k0 + tx * 4 + j;
-      const bool dead = (col >= N) || (row >= N) || (causal && col > row);
+      bool dead = (col >= N) || (row >= N) || (causal && col > row);
+      if (!dead && am_bh) dead = (__ldg(am_bh + (int64_t)row * am_sN + col) == 0) || lse[i] == -INFINITY;
       const float pv = dead ? 0.f : exp2f(fmaf(s[i][j], scale_log2, -lse[i]));
       if (drop_thresh) {
         const bool keep = drop_keep(dkey, row, col, drop_thresh);
@@ -303,6 +314,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
 
   const uint32_t dkey = p.drop.thresh ? drop_key(p.drop, b * p.H + h) : 0u;
   const float dv_mul = p.drop.thresh ? p.drop.rp : 1.0f;
+  const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
   float dk[4][kAcc], dv[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -325,7 +337,8 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
       lse[i] = row < nv ? lsep[row] : 0.f;
       dl[i] = row < nv ? dlp[row] : 0.f;
     }
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp, am_bh,
+              p.am_s[2]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       *reinterpret_cast<float4*>(Ps + (ty * 4 + i) * kSimtLdT + tx * 4) = make_float4(s[i][0], s[i][1], s[i][2], s[i][3]);
@@ -382,6 +395,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
   simt_load_rowmajor<kD>(dOs, SS::kLdR, p.dout + b * p.do_s[0] + h * p.do_s[1] + (int64_t)q0 * p.do_s[2], p.do_s[2],
                          nv - q0);
   const uint32_t dkey = p.drop.thresh ? drop_key(p.drop, b * p.H + h) : 0u;
+  const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
   float lse[4], dl[4], dq[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -402,7 +416,8 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
     float s[4][4], dp[4][4];
     simt_scores_rt<kD>(s, Qs, SS::kLdR, Kt, ty, tx);
     simt_scores_rt<kD>(dp, dOs, SS::kLdR, Vt, ty, tx);
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp, am_bh,
+              p.am_s[2]);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(dSs + (ty * 4 + i) * kSimtLdT + tx * 4) =

@@ -6,6 +6,7 @@ flash_attention_torch.py (FlashAttention :21, FlashAttentionDeterministic :161, 
                                                               # vendored tutorial (_attention.forward :441)
     O = FlashAttention.apply(Q, K, V, causal, softmax_scale, seqlens)   # + per-batch valid lengths (key padding)
     O = FlashAttention.apply(Q, K, V, causal, softmax_scale, seqlens, dropout_p[, dropout_seed])   # + in-kernel dropout
+    O = FlashAttention.apply(Q, K, V, causal, softmax_scale, None, 0.0, None, attn_mask)             # + arbitrary bool mask
 
 Differences from the reference, all deliberate:
   * the kernels are hand-written sm_100a CUDA reached through libfa_b200.so (no Triton, no autotune);
@@ -43,7 +44,8 @@ def _validate(Q, K, V):
 class FlashAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool = False,
-                softmax_scale: float = 1.0, seqlens=None, dropout_p: float = 0.0, dropout_seed=None) -> torch.Tensor:
+                softmax_scale: float = 1.0, seqlens=None, dropout_p: float = 0.0, dropout_seed=None,
+                attn_mask=None) -> torch.Tensor:
         _validate(Q, K, V)
         causal = bool(causal)
         softmax_scale = float(softmax_scale)
@@ -51,14 +53,17 @@ class FlashAttention(torch.autograd.Function):
         if _native.dropout_threshold(dropout_p) and dropout_seed is None:
             # a fresh mask per call, reproducible under torch.manual_seed (drawn from torch's default CPU generator)
             dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if attn_mask is not None and not isinstance(attn_mask, _native.AttentionMask):
+            attn_mask = _native.AttentionMask(attn_mask)   # packed once, reused by the backward
         O, L = _native.forward(Q, K, V, causal, softmax_scale, seqlens=seqlens, dropout_p=dropout_p,
-                               dropout_seed=dropout_seed)   # runs without graph recording
+                               dropout_seed=dropout_seed, attn_mask=attn_mask)   # runs without graph recording
         # same saved set as the reference (flash_attention_torch.py:77), unpadded
         ctx.save_for_backward(Q, K, V, O, L)
         ctx.causal = causal
         ctx.softmax_scale = softmax_scale
         ctx.seqlens = seqlens
         ctx.dropout = (dropout_p, dropout_seed)
+        ctx.attn_mask = attn_mask
         return O
 
     @staticmethod
@@ -68,8 +73,8 @@ class FlashAttention(torch.autograd.Function):
         if Q.dtype != dO.dtype:
             raise ValueError("dO must have same dtype as inputs")
         dQ, dK, dV = _native.backward(Q, K, V, O, dO, L, ctx.causal, ctx.softmax_scale, seqlens=ctx.seqlens,
-                                      dropout_p=ctx.dropout[0], dropout_seed=ctx.dropout[1])
-        return dQ, dK, dV, None, None, None, None, None
+                                      dropout_p=ctx.dropout[0], dropout_seed=ctx.dropout[1], attn_mask=ctx.attn_mask)
+        return dQ, dK, dV, None, None, None, None, None, None
 
 
 # The reference's second Function differs only in which (broken) backward kernel it launches
@@ -78,9 +83,11 @@ FlashAttentionDeterministic = FlashAttention
 
 
 def flash_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0, seqlens=None, dropout_p: float = 0.0,
-                    dropout_seed=None) -> torch.Tensor:
+                    dropout_seed=None, attn_mask=None) -> torch.Tensor:
     """Keyword-friendly front of FlashAttention.apply.  `seqlens` (B,) int: per-batch valid length (key-padding mask,
     the "masking" of the reference's roadmap, README.md:35-37); rows beyond it are zero in O and in the gradients.
     `dropout_p`: in-kernel dropout of the attention probabilities (the "dropout" of the same roadmap), quantised to
-    1/256; `dropout_seed` fixes the mask (default: drawn from torch's CPU generator)."""
-    return FlashAttention.apply(Q, K, V, causal, softmax_scale, seqlens, dropout_p, dropout_seed)
+    1/256; `dropout_seed` fixes the mask (default: drawn from torch's CPU generator).
+    `attn_mask`: arbitrary mask, bool (N, N) / (B|1, N, N) / (B|1, H|1, N, N) or a prepared `AttentionMask`, True = attend,
+    ANDed with `causal` and `seqlens`; queries with no visible key get O = 0 and zero gradients."""
+    return FlashAttention.apply(Q, K, V, causal, softmax_scale, seqlens, dropout_p, dropout_seed, attn_mask)

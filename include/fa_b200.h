@@ -59,11 +59,18 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
  * roadmap (README.md:35-37); float16 / bfloat16 / float32.  The probability is quantised to round(256 p) / 256 (0 = off)
  * and kept entries are scaled by 1 / (1 - that); lse stays the logsumexp of the undropped scores.  The keep mask is a
  * pure function of (dropout_seed, b, h, query, key), restated by the oracle (oracle/attention_oracle.py:
- * dropout_keep_mask); fa_bwd_partial regenerates it from the same (dropout_p, dropout_seed). */
+ * dropout_keep_mask); fa_bwd_partial regenerates it from the same (dropout_p, dropout_seed).
+ * `attn_mask` (device pointer or NULL) is an arbitrary attention mask — the general form of the roadmap's "masking":
+ * one byte per (query, key), non-zero = attend, combined (AND) with `causal` and `seqlens`.  `attn_mask_strides` =
+ * {sB, sH, sRow} in BYTES: sB / sH may be 0 (one mask for all batch elements / heads), the row pitch must be a multiple
+ * of 16 and at least N rounded up to 128 (kernels read whole 16-byte groups of a key block), the base 16-byte aligned.
+ * A query with no visible key gets O = 0, lse = -inf and contributes nothing to the gradients.  float16 / bfloat16 /
+ * float32; with dropout at the same time: float32 only. */
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
-                 void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed, void* stream);
+                 void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                 const uint8_t* attn_mask, const int64_t attn_mask_strides[3], void* stream);
 
 /* Backward preprocess: delta[b,h,i] = sum_d O[b,h,i,d] * dO[b,h,i,d]  (fp32 accumulate).
  * Replaces bwd_D_kernel[grid](...) at flash_attention_torch.py:125-133 and flash_attention_wrappers.py:110-118. */
@@ -95,7 +102,9 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
  * whose dQ part is the spin-locked read-modify-write of flash_attention_kernels.py:305-320; here the two parts are
  * separate kernels, exposed for callers that need only some gradients and for per-kernel timing.  Outputs not
  * selected are left untouched (their pointers must still be valid).  `dropout_p`, `dropout_seed`: the values the forward
- * ran with (two-kernel path only; `delta` must come from the dropped-out O, as fa_bwd_preprocess gives). */
+ * ran with (two-kernel path only; `delta` must come from the dropped-out O, as fa_bwd_preprocess gives).
+ * `attn_mask` as in fa_fwd_peers, plus `attn_mask_t`: the same mask transposed ([.., key, query], same layout rules),
+ * which the dK/dV kernel walks (16-bit dtypes; float32 reads `attn_mask` only and accepts NULL). */
 #define FA_BWD_DKDV 1
 #define FA_BWD_DQ 2
 #define FA_BWD_FUSED 4
@@ -105,7 +114,8 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
-                   void* stream);
+                   const uint8_t* attn_mask, const int64_t attn_mask_strides[3], const uint8_t* attn_mask_t,
+                   const int64_t attn_mask_t_strides[3], void* stream);
 
 /* Sequence-parallel (ring) attention helpers — no counterpart in the reference (single GPU); they sit where a caller that
  * shards the SEQUENCE across GPUs combines what fa_fwd / fa_bwd return for one key / value shard at a time.

@@ -991,3 +991,117 @@ def test_randomized_feature_combinations(case):
             continue
         e = rel_err(got, ref[name])
         assert e <= (3e-4 if dtype == torch.float32 else 1e-2), what + f" {name} rel err {e:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ arbitrary attention mask
+def _run_masked(Q, K, V, dO, causal, scale, mask, seqlens=None, p=0.0, seed=None):
+    q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
+    from flash_attention_dlrs_b200 import AttentionMask
+    am = AttentionMask(mask.to(DEV))
+    O, L = flash_attention_forward(q, k, v, DEV, causal, scale, seqlens, p, seed, am)
+    g = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, seqlens, p, seed, am)
+    g2 = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, seqlens, p, seed, am)
+    torch.cuda.synchronize()
+    for a, b in zip(g, g2):
+        assert torch.equal(a, b)   # deterministic with a mask as well
+    return (O.cpu(), L.cpu()) + tuple(t.cpu() for t in g)
+
+
+def _check_masked(Q, K, V, dO, causal, scale, mask, got, dtype, p=0.0, seed=0):
+    B, H, N, _ = Q.shape
+    O, L, dQ, dK, dV = got
+    keep = orc.dropout_keep_mask(seed, B, H, N, p)
+    ref = orc.attention_dropout_grads_fp64(Q.float(), K.float(), V.float(), dO.float(), scale, causal, keep, p, mask)
+    full = mask.expand(B, H, N, N) & (torch.ones(N, N, dtype=torch.bool).tril() if causal else True)
+    empty = ~full.any(-1)                                              # queries with no visible key
+    assert not O[empty].float().abs().any() and (L.squeeze(-1)[empty] == -math.inf).all()
+    o_err = (O.double() - ref["O"]).abs()
+    seen = ~empty
+    if dtype == torch.float32:
+        assert o_err.max() <= 1e-4 and (L.squeeze(-1)[seen].double() - ref["L"].squeeze(-1)[seen]).abs().max() <= 1e-4
+    else:
+        # P|V| over the visible keys only (an upper bound: the full softmax with |V| is not, the mask renormalises)
+        Pm = torch.softmax((scale * Q.double() @ K.double().transpose(-1, -2)).masked_fill(~full, -math.inf), -1)
+        p_absv = torch.nan_to_num(Pm, nan=0.0) @ V.double().abs()
+        bound = 2e-3 + 2.0 ** -(MANT_BITS[dtype] + 2) * p_absv + out_half_ulp(ref["O"], dtype)
+        assert (o_err <= bound).all(), f"O err {o_err.max().item():.3e}"
+        assert (L.squeeze(-1)[seen].double() - ref["L"].squeeze(-1)[seen]).abs().max() <= 2e-3
+    for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        assert torch.isfinite(g.float()).all(), name
+        e = rel_err(g, ref[name])
+        assert e <= (3e-4 if dtype == torch.float32 else 1e-2), f"{name} rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("kind", ["random", "blocks", "band"])
+def test_attention_mask_parity(dtype, D, causal, kind):
+    """Arbitrary bool masks (True = attend) ANDed with the causal flag: random 70 % dense, block-sparse with whole
+    128 x 128 blocks (and whole query rows) masked out, and a sliding-window band; ragged N; one mask for all heads."""
+    B, H, N = 2, 3, 392
+    g = torch.Generator().manual_seed(5)
+    if kind == "random":
+        mask = torch.rand(B, 1, N, N, generator=g) < 0.7
+        mask[0, 0, 100] = False                                   # a query that sees nothing
+        mask[1, 0, :, 200] = False                                # a key nobody attends to
+    elif kind == "blocks":
+        blk = torch.rand(1, H, 4, 4, generator=g) < 0.5
+        blk[0, :, 2, :] = False                                   # query block 2 of every head is empty
+        blk[0, :, 0, 0] = True
+        mask = blk.repeat_interleave(128, -1).repeat_interleave(128, -2)[..., :N, :N]
+    else:
+        i = torch.arange(N)
+        mask = ((i[:, None] - i[None, :]).abs() <= 37)[None, None]   # (1,1,N,N) sliding window
+    scale = 1.0 / math.sqrt(D)
+    Q, K, V, dO = make_inputs(91, B, H, N, D, dtype)
+    got = _run_masked(Q, K, V, dO, causal, scale, mask)
+    _check_masked(Q, K, V, dO, causal, scale, mask, got, dtype)
+
+
+def test_attention_mask_equivalences_and_autograd():
+    """A tril mask reproduces the causal kernel, an all-True mask the unmasked one (same values up to the exponent
+    polynomial the unmasked forward mixes in); masks given as (N,N) / (B,N,N) / AttentionMask; gradients flow."""
+    B, H, N, D = 2, 2, 300, 128
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(92, B, H, N, D, torch.bfloat16))
+
+    def run(causal, mask):
+        q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+        O = FlashAttention.apply(q, k, v, causal, 0.09, None, 0.0, None, mask)
+        O.backward(dO)
+        return [O.detach().float(), q.grad.float(), k.grad.float(), v.grad.float()]
+
+    tril = torch.ones(N, N, dtype=torch.bool, device=DEV).tril()
+    for a, b in zip(run(True, None), run(False, tril)):
+        assert (a - b).abs().max() <= 2e-2 * b.abs().max()
+    for a, b in zip(run(False, None), run(False, torch.ones(B, N, N, dtype=torch.bool, device=DEV))):
+        assert (a - b).abs().max() <= 2e-2 * b.abs().max()
+    from flash_attention_dlrs_b200 import AttentionMask
+    am = AttentionMask(tril)
+    for a, b in zip(run(False, tril), run(True, am)):     # causal AND tril == tril; packed mask reused
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        FlashAttention.apply(Q, K, V, False, 0.09, None, 0.0, None, torch.ones(N + 1, N + 1, dtype=torch.bool, device=DEV))
+    with pytest.raises(ValueError):
+        FlashAttention.apply(Q, K, V, False, 0.09, None, 0.0, None, torch.ones(3, N, N, dtype=torch.bool, device=DEV))
+    with pytest.raises(_lib.FlashAttentionLibraryError):   # 16-bit: mask and dropout together are not instantiated
+        FlashAttention.apply(Q, K, V, False, 0.09, None, 0.5, 1, tril)
+
+
+def test_attention_mask_with_seqlens_and_fp32_dropout():
+    """mask AND key padding (16-bit); mask AND dropout (float32 kernels take both)."""
+    B, H, N, D = 3, 2, 260, 64
+    g = torch.Generator().manual_seed(6)
+    mask = torch.rand(B, H, N, N, generator=g) < 0.6
+    lens = [260, 131, 40]
+    Q, K, V, dO = make_inputs(93, B, H, N, D, torch.float16)
+    O, L, dQ, dK, dV = _run_masked(Q, K, V, dO, False, 0.125, mask, torch.tensor(lens, dtype=torch.int32))
+    for b, n in enumerate(lens):
+        sub = tuple(t[b:b + 1, :, :n] for t in (Q, K, V, dO))
+        _check_masked(*sub, False, 0.125, mask[b:b + 1, :, :n, :n],
+                      tuple(t[b:b + 1, :, :n] for t in (O, L, dQ, dK, dV)), torch.float16)
+        for t in (O, dQ, dK, dV):
+            assert not t[b, :, n:].float().abs().any()
+    Q, K, V, dO = make_inputs(94, 2, 2, 200, 32, torch.float32)
+    mask = torch.rand(2, 1, 200, 200, generator=g) < 0.5
+    got = _run_masked(Q, K, V, dO, True, 0.2, mask, None, 0.3, 777)
+    _check_masked(Q, K, V, dO, True, 0.2, mask, got, torch.float32, 0.3, 777)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 4
+    assert lib.fa_version() == 5
     assert isinstance(lib.fa_last_error(), bytes)
 
 
@@ -232,10 +232,25 @@ def test_c_abi_rejects_bad_dropout_arguments():
     s = (ctypes.c_int64 * 4)(64 * 128, 128 * 64, 64, 1)
     null = ctypes.c_void_p(0)
     peers = (ctypes.c_void_p * 1)()
-    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 1.0, 0, null)
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 1.0, 0,
+                          null, None, null)
     assert rc < 0 and b"dropout_p" in lib.fa_last_error()
-    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.5, 0, null)
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.5, 0,
+                          null, None, null)
     assert rc < 0 and b"FP8" in lib.fa_last_error()
     rc = lib.fa_bwd_partial(null, null, null, null, null, null, null, null, null, null, 0, 1, 1, 128, 64, s, s, s, s, s, s, s,
-                            1, 1.0, 0, 4, null, 0.5, 0, null)
+                            1, 1.0, 0, 4, null, 0.5, 0, null, None, null, None, null)
     assert rc < 0 and b"FA_BWD_FUSED" in lib.fa_last_error()
+    # attention mask: row pitch must cover N rounded up to 128 and keep 16-byte groups aligned
+    ms = (ctypes.c_int64 * 3)(0, 0, 100)
+    fake = ctypes.c_void_p(4096)
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 0.0, 0,
+                          fake, ms, null)
+    assert rc < 0 and b"row pitch" in lib.fa_last_error()
+    ms = (ctypes.c_int64 * 3)(0, 0, 128)
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.0, 0,
+                          fake, ms, null)
+    assert rc < 0 and b"FP8" in lib.fa_last_error()
+    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 0.5, 1,
+                          fake, ms, null)
+    assert rc < 0 and b"float32 only" in lib.fa_last_error()
