@@ -819,10 +819,11 @@ def test_bnhd_storage_viewed_as_bhnd_needs_no_copy_and_matches():
 
 
 # ------------------------------------------------------------------------------------------------ in-kernel dropout
-def _run_dropout(Q, K, V, dO, causal, scale, p, seed, seqlens=None):
+def _run_dropout(Q, K, V, dO, causal, scale, p, seed, seqlens=None, mask=None):
     q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
-    O, L = flash_attention_forward(q, k, v, DEV, causal, scale, seqlens, p, seed)
-    g = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, seqlens, p, seed)
+    mask = None if mask is None else mask.to(DEV)
+    O, L = flash_attention_forward(q, k, v, DEV, causal, scale, seqlens, p, seed, mask)
+    g = flash_attention_backward(q, k, v, O, do, L, DEV, True, causal, scale, seqlens, p, seed, mask)
     torch.cuda.synchronize()
     return (O.cpu(), L.cpu()) + tuple(t.cpu() for t in g)
 
@@ -944,10 +945,11 @@ def test_dropout_autograd_seeding_and_determinism():
 
 
 # ------------------------------------------------------------------------------------------------ randomized combinations
-@pytest.mark.parametrize("case", range(24))
+@pytest.mark.parametrize("case", range(40))
 def test_randomized_feature_combinations(case):
     """Seeded random draws over everything the default path takes at once — dtype, head size (padded or not), ragged N,
-    causal, scale, per-batch lengths, dropout — against the float64 closed form evaluated per batch element."""
+    causal, scale, per-batch lengths, dropout, an arbitrary mask (16-bit: not together with dropout) — against the
+    float64 closed form evaluated per batch element."""
     rng = np.random.default_rng(1000 + case)
     dtype = (torch.bfloat16, torch.float16, torch.float32)[case % 3]
     d = int(rng.choice([16, 24, 40, 64, 72, 128]))
@@ -958,12 +960,18 @@ def test_randomized_feature_combinations(case):
     p = float(rng.choice([0.0, 0.0, 0.1, 0.5]))
     seed = int(rng.integers(0, 2 ** 62))
     lens = [int(x) for x in rng.integers(0, N + 1, size=B)] if rng.integers(0, 2) else None
+    mask = None
+    if rng.integers(0, 2) and (p == 0.0 or dtype == torch.float32):
+        shape = [(N, N), (B, N, N), (1, H, N, N), (B, H, N, N)][int(rng.integers(0, 4))]
+        mask = torch.from_numpy(rng.random(shape) < 0.75)
+        mask4 = mask.reshape((1,) * (4 - mask.dim()) + tuple(mask.shape)) if mask.dim() != 3 else mask[:, None]
     Q, K, V, dO = make_inputs(2000 + case, B, H, N, d, dtype)
     sl = None if lens is None else torch.tensor(lens, dtype=torch.int32)
-    O, L, dQ, dK, dV = _run_dropout(Q, K, V, dO, causal, scale, p, seed, sl)
+    O, L, dQ, dK, dV = _run_dropout(Q, K, V, dO, causal, scale, p, seed, sl, mask)
     keep = orc.dropout_keep_mask(seed, B, H, N, p)
     rp = 256.0 / (256.0 - orc.dropout_threshold(p))
-    what = f"case {case}: {dtype} d={d} N={N} B={B} H={H} causal={causal} scale={scale:.3f} p={p} lens={lens}"
+    what = (f"case {case}: {dtype} d={d} N={N} B={B} H={H} causal={causal} scale={scale:.3f} p={p} lens={lens} "
+            f"mask={None if mask is None else tuple(mask.shape)}")
     ref = {k: torch.zeros(Q.shape, dtype=torch.float64) for k in ("O", "dQ", "dK", "dV")}
     ref["L"] = torch.zeros(B, H, N, 1, dtype=torch.float64)
     bound = torch.zeros(Q.shape, dtype=torch.float64)
@@ -972,15 +980,22 @@ def test_randomized_feature_combinations(case):
         if n == 0:
             continue
         qb, kb, vb, dob = (t[b:b + 1, :, :n].float() for t in (Q, K, V, dO))
-        r = orc.attention_dropout_grads_fp64(qb, kb, vb, dob, scale, causal, keep[b:b + 1, :, :n, :n], p)
+        mb = None if mask is None else mask4[(b if mask4.shape[0] > 1 else 0):(b if mask4.shape[0] > 1 else 0) + 1, :, :n, :n]
+        r = orc.attention_dropout_grads_fp64(qb, kb, vb, dob, scale, causal, keep[b:b + 1, :, :n, :n], p, mb)
         for k in ref:
-            ref[k][b:b + 1, :, :n] = r[k]
+            ref[k][b:b + 1, :, :n] = torch.nan_to_num(r[k], neginf=0.0) if k == "L" else r[k]
         if dtype != torch.float32:
-            p_absv = orc.reference_sdpa(qb, kb, vb.abs(), scale, causal).double()
-            bound[b:b + 1, :, :n] = rp * (2e-3 + 2.0 ** -(MANT_BITS[dtype] + 2) * p_absv) + out_half_ulp(r["O"], dtype)
+            vis = torch.ones(n, n, dtype=torch.bool).tril() if causal else torch.ones(n, n, dtype=torch.bool)
+            vis = vis if mb is None else (vis & mb)
+            Pm = torch.softmax((scale * qb.double() @ kb.double().transpose(-1, -2)).masked_fill(~vis, -math.inf), -1)
+            p_absv = torch.nan_to_num(Pm, nan=0.0) @ vb.double().abs()
+            # worst-case rounding of P to the input dtype (relative 2^-(mant+1)): with the sharp softmaxes drawn here one
+            # key can carry the whole row, so the rounding errors do not average out as in the fixed-scale tests above
+            bound[b:b + 1, :, :n] = rp * (2e-3 + 2.0 ** -(MANT_BITS[dtype] + 1) * p_absv) + out_half_ulp(r["O"], dtype)
         else:
             bound[b:b + 1, :, :n] = 1e-4 * rp
     assert ((O.double() - ref["O"]).abs() <= bound).all(), what + f" O err {(O.double() - ref['O']).abs().max():.3e}"
+    L = torch.nan_to_num(L, neginf=0.0)   # queries with no visible key: L = -inf on both sides
     assert (L.double() - ref["L"]).abs().max() <= (1e-4 if dtype == torch.float32 else 2e-3), what
     for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
         if ref[name].abs().max() < 1e-9:
