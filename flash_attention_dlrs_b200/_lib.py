@@ -84,6 +84,14 @@ _lock = threading.Lock()
 _lib = None
 
 _I64x4 = ctypes.c_int64 * 4
+_I64x3 = ctypes.c_int64 * 3
+
+
+class AttnMaskStruct(ctypes.Structure):
+    """fa_attn_mask of include/fa_b200.h."""
+    _fields_ = [("rows", ctypes.c_void_p), ("rows_strides", _I64x3),
+                ("cols", ctypes.c_void_p), ("cols_strides", _I64x3),
+                ("blocks", ctypes.c_void_p), ("blocks_strides", _I64x3)]
 
 
 def _declare(lib):
@@ -97,7 +105,7 @@ def _declare(lib):
     lib.fa_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, vp]
     lib.fa_fwd_peers.restype = i
     lib.fa_fwd_peers.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, st, st, st, st, i, f, i, i, ctypes.POINTER(vp), vp,
-                                 f, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_int64), vp]
+                                 f, ctypes.c_uint64, ctypes.POINTER(AttnMaskStruct), vp]
     lib.fa_bwd_preprocess.restype = i
     lib.fa_bwd_preprocess.argtypes = [vp, vp, vp, i, i, i, i, st, st, i, vp]
     lib.fa_bwd_workspace_bytes.restype = sz
@@ -106,8 +114,7 @@ def _declare(lib):
     lib.fa_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i, vp]
     lib.fa_bwd_partial.restype = i
     lib.fa_bwd_partial.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, st, st, st, st, st, st, st, i, f, i,
-                                   i, vp, f, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_int64), vp,
-                                   ctypes.POINTER(ctypes.c_int64), vp]
+                                   i, vp, f, ctypes.c_uint64, ctypes.POINTER(AttnMaskStruct), vp]
 
 
 def _declare_ring(lib):

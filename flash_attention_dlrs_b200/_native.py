@@ -144,27 +144,37 @@ class AttentionMask:
             return buf
 
         self.rows, self.cols = pack(m), pack(m.transpose(-1, -2))
+        # 128 x 128 block summary: blocks[.., i, j] = some entry of block (i, j) is visible; the kernels skip the others
+        nb = pitch // 128
+        sq = torch.zeros((Bm, Hm, pitch, pitch), dtype=torch.bool, device=m.device)
+        sq[..., :N, :N] = m
+        self.blocks = sq.view(Bm, Hm, nb, 128, nb, 128).any(-1).any(-2).to(torch.uint8).contiguous()
         self.shape = (Bm, Hm, N)
+        self._struct = None
 
-    def args(self, B: int, H: int, N: int, device):
-        """(rows ptr, rows strides, cols ptr, cols strides) for a (B, H, N, .) problem; size-1 dims broadcast."""
+    def struct(self, B: int, H: int, N: int, device):
+        """ctypes fa_attn_mask for a (B, H, N, .) problem; size-1 batch / head dims broadcast (stride 0)."""
         Bm, Hm, Nm = self.shape
         if Nm != N or Bm not in (1, B) or Hm not in (1, H):
             raise ValueError(f"attn_mask of shape {(Bm, Hm, Nm, Nm)} does not broadcast to {(B, H, N, N)}")
         if self.rows.device != device:
             raise ValueError(f"attn_mask is on {self.rows.device}, the inputs on {device}")
-        out = []
-        for t in (self.rows, self.cols):
-            sB, sH, sN, _ = t.stride()
-            out += [_ptr(t), (ctypes.c_int64 * 3)(0 if Bm == 1 else sB, 0 if Hm == 1 else sH, sN)]
-        return out
+        if self._struct is None:
+            st = _lib.AttnMaskStruct()
+            for name, t in (("rows", self.rows), ("cols", self.cols), ("blocks", self.blocks)):
+                sB, sH, sN, _ = t.stride()
+                setattr(st, name, t.data_ptr())
+                setattr(st, name + "_strides", _lib._I64x3(0 if Bm == 1 else sB, 0 if Hm == 1 else sH, sN))
+            self._struct = st
+        return self._struct
 
 
 def _mask_arg(attn_mask, B, H, N, device):
+    """(AttentionMask kept alive, pointer to its fa_attn_mask or NULL)"""
     if attn_mask is None:
-        return None, [ctypes.c_void_p(0), None, ctypes.c_void_p(0), None]
+        return None, None
     am = attn_mask if isinstance(attn_mask, AttentionMask) else AttentionMask(attn_mask)
-    return am, am.args(B, H, N, device)
+    return am, ctypes.byref(am.struct(B, H, N, device))
 
 
 def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, softmax_scale: float, out=None,
@@ -215,7 +225,7 @@ def forward(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool, sof
         rc = lib.fa_fwd_peers(_ptr(q), _ptr(k), _ptr(v), o_ptr, _ptr(L), B, H, N, d_run,
                               _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), o_strides,
                               code, float(softmax_scale), int(bool(causal)), len(peer_ptrs), peers, sl_ptr,
-                              drop_p, drop_seed, am_args[0], am_args[1], _stream_ptr(Q.device))
+                              drop_p, drop_seed, am_args, _stream_ptr(Q.device))
     _lib.check(rc, "fa_fwd")
     if O is None:
         return None, L
@@ -276,7 +286,7 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
                                 d_run, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),
                                 _lib.strides4(dQ), _lib.strides4(dK), _lib.strides4(dV),
                                 code, float(softmax_scale), int(bool(causal)), int(which), sl_ptr,
-                                drop_p, drop_seed, *am_args, _stream_ptr(Q.device))
+                                drop_p, drop_seed, am_args, _stream_ptr(Q.device))
     _lib.check(rc, "fa_bwd")
     if d_run != d:
         dQ, dK, dV = dQ[..., :d], dK[..., :d], dV[..., :d]

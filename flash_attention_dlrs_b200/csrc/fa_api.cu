@@ -92,6 +92,14 @@ int check_amask(const char* fn, const char* name, const uint8_t* m, const int64_
   return 0;
 }
 
+// 128 x 128 block summary of a mask: bytes [.., query block, key block], strides {sB, sH, sI} in bytes
+int check_ablock(const char* fn, const fa_attn_mask* m) {
+  if (!m || !m->blocks) return 0;
+  const int64_t* s = m->blocks_strides;
+  if (s[0] < 0 || s[1] < 0 || s[2] <= 0) return fail(-14, "%s: attn_mask->blocks strides must be non-negative (row stride positive)", fn);
+  return 0;
+}
+
 void fill3(int64_t (&dst)[3], const int64_t s[4]) {
   dst[0] = s[0], dst[1] = s[1], dst[2] = s[2];
 }
@@ -228,7 +236,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 5; }
+int fa_version(void) { return 6; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -236,16 +244,20 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
            const int64_t o_strides[4], int dtype, float softmax_scale, int causal, void* stream) {
   return fa_fwd_peers(q, k, v, o, lse, B, H, N, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale,
-                      causal, 0, nullptr, nullptr, 0.f, 0, nullptr, nullptr, stream);
+                      causal, 0, nullptr, nullptr, 0.f, 0, nullptr, stream);
 }
 
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
                  void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
-                 const uint8_t* attn_mask, const int64_t attn_mask_strides[3], void* stream) {
+                 const fa_attn_mask* mask, void* stream) {
   g_err[0] = 0;
-  if (int r = check_amask("fa_fwd_peers", "attn_mask", attn_mask, attn_mask_strides, N)) return r;
+  if (mask && !mask->rows) return fail(-14, "fa_fwd_peers: attn_mask->rows is null");
+  const uint8_t* attn_mask = mask ? mask->rows : nullptr;
+  const int64_t* attn_mask_strides = mask ? mask->rows_strides : nullptr;
+  if (int r = check_amask("fa_fwd_peers", "attn_mask->rows", attn_mask, attn_mask_strides, N)) return r;
+  if (int r = check_ablock("fa_fwd_peers", mask)) return r;
   if (attn_mask && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
     return fail(-14, "fa_fwd_peers: attention masks are not implemented for the FP8 forward");
   fa::DropParams drop;
@@ -278,6 +290,10 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
     p.drop = drop;
     p.amask = attn_mask;
     if (attn_mask) p.am_s[0] = attn_mask_strides[0], p.am_s[1] = attn_mask_strides[1], p.am_s[2] = attn_mask_strides[2];
+    if (mask && mask->blocks) {
+      p.ablock = mask->blocks;
+      for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
+    }
     switch (D) {
       case 16: return launch_fwd32<16>(p, st);
       case 32: return launch_fwd32<32>(p, st);
@@ -307,6 +323,8 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   p.drop = drop;
   p.amask = attn_mask;
   if (attn_mask) p.am_sB = attn_mask_strides[0], p.am_sH = attn_mask_strides[1], p.am_sN = attn_mask_strides[2];
+  if (mask && mask->blocks)
+    p.ablock = mask->blocks, p.ab_sB = mask->blocks_strides[0], p.ab_sH = mask->blocks_strides[1], p.ab_sI = mask->blocks_strides[2];
 #define FA_FWD_CASE(E, DD, C) \
   if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
   FA_FWD_CASE(FA_DTYPE_BF16, 128, true)
@@ -374,7 +392,7 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
   // the single-pass kernel, whose dQ reduction is bound by the SM -> L2 path.
   return fa_bwd_partial(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, D, q_strides,
                         k_strides, v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale,
-                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, 0.f, 0, nullptr, nullptr, nullptr, nullptr, stream);
+                        causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, 0.f, 0, nullptr, stream);
 }
 
 int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
@@ -383,16 +401,20 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
-                   const uint8_t* attn_mask, const int64_t attn_mask_strides[3], const uint8_t* attn_mask_t,
-                   const int64_t attn_mask_t_strides[3], void* stream) {
+                   const fa_attn_mask* mask, void* stream) {
   g_err[0] = 0;
-  if (int r = check_amask("fa_bwd_partial", "attn_mask", attn_mask, attn_mask_strides, N)) return r;
-  if (int r = check_amask("fa_bwd_partial", "attn_mask_t", attn_mask_t, attn_mask_t_strides, N)) return r;
+  if (mask && !mask->rows) return fail(-14, "fa_bwd_partial: attn_mask->rows is null");
+  const uint8_t* attn_mask = mask ? mask->rows : nullptr;
+  const uint8_t* attn_mask_t = mask ? mask->cols : nullptr;
+  const int64_t* attn_mask_strides = mask ? mask->rows_strides : nullptr;
+  const int64_t* attn_mask_t_strides = mask ? mask->cols_strides : nullptr;
+  if (int r = check_amask("fa_bwd_partial", "attn_mask->rows", attn_mask, attn_mask_strides, N)) return r;
+  if (int r = check_amask("fa_bwd_partial", "attn_mask->cols", attn_mask_t, attn_mask_t_strides, N)) return r;
+  if (int r = check_ablock("fa_bwd_partial", mask)) return r;
   if (attn_mask && which == FA_BWD_FUSED)
     return fail(-14, "fa_bwd_partial: FA_BWD_FUSED takes no attention mask; use the two-kernel path");
   if (attn_mask && !attn_mask_t && dtype != FA_DTYPE_F32)
-    return fail(-14, "fa_bwd_partial: the 16-bit kernels need the transposed mask (attn_mask_t) as well");
-  if ((bool)attn_mask_t && !attn_mask) return fail(-14, "fa_bwd_partial: attn_mask_t given without attn_mask");
+    return fail(-14, "fa_bwd_partial: the 16-bit kernels need the transposed mask (attn_mask->cols) as well");
   fa::DropParams drop;
   if (int r = make_drop("fa_bwd_partial", dropout_p, dropout_seed, &drop)) return r;
   if (drop.thresh && which == FA_BWD_FUSED)
@@ -437,6 +459,10 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
     p.drop = drop;
     p.amask = attn_mask;
     if (attn_mask) p.am_s[0] = attn_mask_strides[0], p.am_s[1] = attn_mask_strides[1], p.am_s[2] = attn_mask_strides[2];
+    if (mask && mask->blocks) {
+      p.ablock = mask->blocks;
+      for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
+    }
     switch (D) {
       case 16: return launch_bwd32<16>(p, which, st);
       case 32: return launch_bwd32<32>(p, which, st);
@@ -465,6 +491,10 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   p.amask = attn_mask, p.amask_t = attn_mask_t;
   if (attn_mask) {
     for (int i = 0; i < 3; ++i) p.am_s[i] = attn_mask_strides[i], p.amt_s[i] = attn_mask_t_strides[i];
+    if (mask->blocks) {
+      p.ablock = mask->blocks;
+      for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
+    }
   }
 #define FA_BWD_CASE(BF, DD, C)                                                                  \
   if (bf == BF && D == DD && (causal != 0) == C)                                                \

@@ -64,6 +64,13 @@ struct FwdParams {
   // key gives O = 0, L = -inf.
   const uint8_t* amask;
   int64_t am_sB, am_sH, am_sN;
+  // Optional block summary of the mask: ablock[.., i, j] != 0 iff some (query, key) of the 128 x 128 block (i, j) is
+  // visible.  Blocks flagged 0 are skipped: the S / P / O barriers keep their per-block traffic (so that part of the
+  // protocol is the one of the dense kernel) but no MMAs are issued and no softmax work is done for them, and a key block
+  // that neither query tile of the CTA needs is not loaded at all (the K / V ring is indexed by the count of loaded
+  // blocks).  nullptr, or more than 512 key blocks: no skipping.
+  const uint8_t* ablock;
+  int64_t ab_sB, ab_sH, ab_sI;
 };
 
 // kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
@@ -106,6 +113,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __shared__ uint64_t q_full[2], s_full[2], p_full[2][2], o_full[2];
   __shared__ uint64_t k_full[NS], k_empty[NS], v_full[NS], v_empty[NS];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint8_t s_act[2][kAmask ? 512 : 4];   // kAmask: block (tile t, key block j) has a visible entry
+  __shared__ uint16_t s_ld[kAmask ? 512 : 2];      // kAmask: position of key block j among the loaded blocks (0xffff: not loaded)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,6 +134,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     nkv[t] = (t < ntiles) ? n : 0;
   }
   const int nkv_max = max(nkv[0], nkv[1]);
+  const bool use_act = kAmask && p.ablock != nullptr && n_kv_total <= 512;
+  if constexpr (kAmask) {
+    if (use_act) {
+      for (int t = 0; t < 2; ++t) {
+        const uint8_t* ab = p.ablock + (int64_t)b * p.ab_sB + (int64_t)h * p.ab_sH + (int64_t)(2 * qb + t) * p.ab_sI;
+        for (int j = threadIdx.x; j < nkv[t]; j += blockDim.x) s_act[t][j] = ab[j];
+      }
+      __syncthreads();   // (use_act is uniform over the CTA)
+      if (threadIdx.x == 0) {
+        int c = 0;
+        for (int j = 0; j < nkv_max; ++j) {
+          const bool ld = (j < nkv[0] && s_act[0][j]) || (j < nkv[1] && s_act[1][j]);
+          s_ld[j] = ld ? (uint16_t)c : (uint16_t)0xffff;
+          c += ld;
+        }
+      }
+    }
+  }
+  // (both published by the __syncthreads below)
+  auto active = [&](int t, int j) -> bool { return !use_act || s_act[t][j] != 0; };
+  auto load_index = [&](int j) -> int { return use_act ? (int)s_ld[j] : j; };   // 0xffff: key block j is not loaded
 
   if (threadIdx.x == 0) {
     for (int t = 0; t < 2; ++t) {
@@ -165,8 +195,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                       b);
       }
       for (int j = 0; j < nkv_max; ++j) {
-        const int s = j % NS;
-        const uint32_t ph = (j / NS) & 1;
+        const int idx = kAmask ? load_index(j) : j;
+        if (kAmask && idx == 0xffff) continue;   // no tile of this CTA needs key block j
+        const int s = idx % NS;
+        const uint32_t ph = (idx / NS) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
@@ -190,58 +222,72 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       auto tO = [&](int t) { return tmem + (t ? Cfg::kTmemO1 : Cfg::kTmemO0); };
 
       auto issue_s = [&](int t, int j) {
-        const int s = j % NS;
-        mbar_wait(&k_full[s], (j / NS) & 1);
-        tc_fence_after();
+        const int idx = kAmask ? load_index(j) : j;
+        const bool loaded = !kAmask || idx != 0xffff;
+        const int s = idx % NS;
         const uint32_t a0 = qlo + t * kTileLo, b0 = klo + s * kTileLo, d0 = tS(t);
-        static_for<0, Cfg::kSteps>([&](auto kc) {
-          constexpr int k = decltype(kc)::value;
-          constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
-          if constexpr (kF8)
-            umma8_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
-          else
-            umma_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
-        });
+        if (!kAmask || active(t, j)) {
+          mbar_wait(&k_full[s], (idx / NS) & 1);
+          tc_fence_after();
+          static_for<0, Cfg::kSteps>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+            if constexpr (kF8)
+              umma8_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
+            else
+              umma_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
+          });
+        }
         tc_commit(&s_full[t]);
         // last tile that reads K block j releases the stage
         const bool last_user = (t == 1) || (nkv[1] <= j);
-        if (last_user) tc_commit(&k_empty[s]);
+        if (last_user && loaded) tc_commit(&k_empty[s]);
       };
 
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(&q_full[t], 0);
         issue_s(t, 0);
       }
+      bool pv_started[2] = {false, false};   // kAmask: the first P.V of a tile that is not skipped initialises O
       for (int j = 0; j < nkv_max; ++j) {
-        const int s = j % NS;
+        const int idx = kAmask ? load_index(j) : j;
+        const bool loaded = !kAmask || idx != 0xffff;
+        const int s = idx % NS;
         for (int t = 0; t < ntiles; ++t) {
           if (j >= nkv[t]) continue;
-          mbar_wait(&v_full[s], (j / NS) & 1);
+          if (!kAmask || active(t, j)) mbar_wait(&v_full[s], (idx / NS) & 1);
           // P arrives in two 64-key halves so the first half of P·V overlaps the second half of the exponentials
           const uint32_t dO_t = tO(t), aP = tS(t), bV = vlo + s * kTileLo;
           // 16-bit P: 16 keys = 8 TMEM columns and 2048 bytes of V per MMA; FP8 P: 32 keys = 8 columns and 4096 bytes
           constexpr int kPSteps = kF8 ? 4 : 8, kVStep = kF8 ? 2 : 1;
+          const bool act = !kAmask || active(t, j);
+          const bool acc0 = kAmask ? pv_started[t] : (j > 0);
           mbar_wait(&p_full[t][0], j & 1);
           tc_fence_after();
-          static_for<0, kPSteps / 2>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            if constexpr (kF8)
-              umma8_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, (j > 0) || (k > 0));
-            else
-              umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, (j > 0) || (k > 0));
-          });
+          if (act) {
+            static_for<0, kPSteps / 2>([&](auto kc) {
+              constexpr int k = decltype(kc)::value;
+              if constexpr (kF8)
+                umma8_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, acc0 || (k > 0));
+              else
+                umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, acc0 || (k > 0));
+            });
+          }
           mbar_wait(&p_full[t][1], j & 1);
           tc_fence_after();
-          static_for<kPSteps / 2, kPSteps>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            if constexpr (kF8)
-              umma8_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
-            else
-              umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
-          });
+          if (act) {
+            static_for<kPSteps / 2, kPSteps>([&](auto kc) {
+              constexpr int k = decltype(kc)::value;
+              if constexpr (kF8)
+                umma8_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
+              else
+                umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
+            });
+            pv_started[t] = true;
+          }
           tc_commit(&o_full[t]);
           const bool last_user = (t == 1) || (nkv[1] <= j);
-          if (last_user) tc_commit(&v_empty[s]);
+          if (last_user && loaded) tc_commit(&v_empty[s]);
           if (j + 1 < nkv[t]) issue_s(t, j + 1);
         }
       }
@@ -271,9 +317,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       am_row = p.amask + (int64_t)b * p.am_sB + (int64_t)h * p.am_sH + (int64_t)min(q_row, p.N - 1) * p.am_sN;
 
     float m_used = -INFINITY, l = 0.f;
+    bool seen_block = false;   // kAmask: some key block of this tile was not skipped (O has been written)
     for (int j = 0; j < my_nkv; ++j) {
       uint4 mk[kAmask ? 8 : 1];   // this row's 128 mask bytes of key block j, requested before the wait for S
       if constexpr (kAmask) {
+        if (!active(t, j)) {   // skipped block: keep the barrier protocol, do no work
+          mbar_wait(&s_full[t], j & 1);
+          tc_fence_before();
+          mbar_arrive(&p_full[t][0]);
+          mbar_arrive(&p_full[t][1]);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
       }
@@ -319,7 +373,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
       }
       const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
-      if (j == 0) {
+      const bool first_block = kAmask ? !seen_block : (j == 0);
+      seen_block = true;
+      if (first_block) {
         m_used = m_new;
       } else {
         const bool need = (m_new - m_used) * sl2 > 8.0f;
@@ -441,6 +497,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         uint32_t orr[32];
         tmem_ld_x32(tO + c * 32, orr);
         tc_wait_ld();
+        if (kAmask && !seen_block) {   // every key block of this tile was skipped: O was never written
+#pragma unroll
+          for (int i = 0; i < 32; ++i) orr[i] = 0u;
+        }
         if constexpr (!kF8) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {

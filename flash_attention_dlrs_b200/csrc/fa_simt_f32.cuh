@@ -33,6 +33,8 @@ struct SimtParams {
   // arbitrary attention mask, bytes [.., query, key], non-zero = attend (nullptr: none); strides in bytes, sB / sH may be 0
   const uint8_t* amask;
   int64_t am_s[3];
+  const uint8_t* ablock;   // optional 128 x 128 block summary [.., query block, key block]: 0 = nothing visible, skip
+  int64_t ab_s[3];
 };
 
 __device__ __forceinline__ bool simt_visible(const uint8_t* am_bh, int64_t am_sN, int row, int col) {
@@ -197,8 +199,10 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
   const uint32_t dkey = drop_thresh ? drop_key(p.drop, b * p.H + h) : 0u;
   const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
   const int n_kv = p.causal ? min((nv + 63) / 64, qb + 1) : (nv + 63) / 64;
+  const uint8_t* ab_q = p.ablock ? p.ablock + b * p.ab_s[0] + h * p.ab_s[1] + (int64_t)(q0 >> 7) * p.ab_s[2] : nullptr;
   for (int jb = 0; jb < n_kv; ++jb) {
     const int k0 = jb * 64;
+    if (ab_q && !ab_q[k0 >> 7]) continue;   // nothing visible in this block (uniform over the CTA)
     __syncthreads();  // previous iteration's readers of Kt / Vs / Ps are done (also covers the Qt fill)
     simt_load_transposed<kD>(Kt, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
     simt_load_rowmajor<kD>(Vs, kD, vp + (int64_t)k0 * p.v_s[2], p.v_s[2], nv - k0);
@@ -322,8 +326,10 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
     for (int j = 0; j < kAcc; ++j) dk[i][j] = 0.f, dv[i][j] = 0.f;
 
   const int n_q = (nv + 63) / 64;
+  const uint8_t* ab_k = p.ablock ? p.ablock + b * p.ab_s[0] + h * p.ab_s[1] + (k0 >> 7) : nullptr;
   for (int ib = p.causal ? jb : 0; ib < n_q; ++ib) {
     const int q0 = ib * 64;
+    if (ab_k && !ab_k[(int64_t)(q0 >> 7) * p.ab_s[2]]) continue;   // nothing visible in this block
     __syncthreads();
     simt_load_rowmajor<kD>(Qs, SS::kLdR, qp + (int64_t)q0 * p.q_s[2], p.q_s[2], nv - q0);
     simt_load_rowmajor<kD>(dOs, SS::kLdR, dop + (int64_t)q0 * p.do_s[2], p.do_s[2], nv - q0);
@@ -406,8 +412,10 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
     for (int j = 0; j < kAcc; ++j) dq[i][j] = 0.f;
   }
   const int n_kv = p.causal ? min((nv + 63) / 64, ib + 1) : (nv + 63) / 64;
+  const uint8_t* ab_q = p.ablock ? p.ablock + b * p.ab_s[0] + h * p.ab_s[1] + (int64_t)(q0 >> 7) * p.ab_s[2] : nullptr;
   for (int jb = 0; jb < n_kv; ++jb) {
     const int k0 = jb * 64;
+    if (ab_q && !ab_q[k0 >> 7]) continue;   // nothing visible in this block
     __syncthreads();
     simt_load_transposed<kD>(Kt, kp + (int64_t)k0 * p.k_s[2], p.k_s[2], nv - k0);
     simt_load_transposed<kD>(Vt, vp + (int64_t)k0 * p.v_s[2], p.v_s[2], nv - k0);

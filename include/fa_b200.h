@@ -34,6 +34,25 @@ extern "C" {
 #define FA_DTYPE_F8E4M3 3 /* forward only, D = 128 */
 #define FA_DTYPE_F8E5M2 4 /* forward only, D = 128; the FP8 type of the reference's dtype map, flash_attention_torch.py:15-16 */
 
+/* An arbitrary attention mask (the general form of the "masking" on the reference's roadmap, README.md:35-37), ANDed with
+ * `causal` and `seqlens`.  All pointers are device pointers to BYTES, non-zero = attend; strides are {sB, sH, sRow} in
+ * bytes, sB / sH may be 0 (one mask for all batch elements / heads).
+ *   rows   [.., query, key]: read by the forward and the dQ kernel.  Row pitch a multiple of 16 and at least N rounded up
+ *          to 128 (kernels read whole 16-byte groups of a 128-key block), base 16-byte aligned.
+ *   cols   [.., key, query]: the same mask transposed, same layout rules; read by the dK/dV kernel (16-bit dtypes;
+ *          float32 reads `rows` only and accepts NULL).  Not used by the forward.
+ *   blocks [.., query block, key block] (128 x 128 blocks), optional (NULL = none): 0 = no visible entry in the block.
+ *          Such blocks are skipped (no MMAs, no softmax work); with up to 512 blocks per row / column.
+ * A query with no visible key gets O = 0, lse = -inf and contributes nothing to the gradients. */
+typedef struct fa_attn_mask {
+  const uint8_t* rows;
+  int64_t rows_strides[3];
+  const uint8_t* cols;
+  int64_t cols_strides[3];
+  const uint8_t* blocks;
+  int64_t blocks_strides[3];
+} fa_attn_mask;
+
 /* ABI version of this header (bumped on any signature change). */
 int fa_version(void);
 
@@ -60,17 +79,13 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
  * and kept entries are scaled by 1 / (1 - that); lse stays the logsumexp of the undropped scores.  The keep mask is a
  * pure function of (dropout_seed, b, h, query, key), restated by the oracle (oracle/attention_oracle.py:
  * dropout_keep_mask); fa_bwd_partial regenerates it from the same (dropout_p, dropout_seed).
- * `attn_mask` (device pointer or NULL) is an arbitrary attention mask — the general form of the roadmap's "masking":
- * one byte per (query, key), non-zero = attend, combined (AND) with `causal` and `seqlens`.  `attn_mask_strides` =
- * {sB, sH, sRow} in BYTES: sB / sH may be 0 (one mask for all batch elements / heads), the row pitch must be a multiple
- * of 16 and at least N rounded up to 128 (kernels read whole 16-byte groups of a key block), the base 16-byte aligned.
- * A query with no visible key gets O = 0, lse = -inf and contributes nothing to the gradients.  float16 / bfloat16 /
- * float32; with dropout at the same time: float32 only. */
+ * `attn_mask` (NULL = none): an arbitrary attention mask, see fa_attn_mask above.  float16 / bfloat16 / float32; with
+ * dropout at the same time: float32 only. */
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
                  void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
-                 const uint8_t* attn_mask, const int64_t attn_mask_strides[3], void* stream);
+                 const fa_attn_mask* attn_mask, void* stream);
 
 /* Backward preprocess: delta[b,h,i] = sum_d O[b,h,i,d] * dO[b,h,i,d]  (fp32 accumulate).
  * Replaces bwd_D_kernel[grid](...) at flash_attention_torch.py:125-133 and flash_attention_wrappers.py:110-118. */
@@ -103,8 +118,7 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
  * separate kernels, exposed for callers that need only some gradients and for per-kernel timing.  Outputs not
  * selected are left untouched (their pointers must still be valid).  `dropout_p`, `dropout_seed`: the values the forward
  * ran with (two-kernel path only; `delta` must come from the dropped-out O, as fa_bwd_preprocess gives).
- * `attn_mask` as in fa_fwd_peers, plus `attn_mask_t`: the same mask transposed ([.., key, query], same layout rules),
- * which the dK/dV kernel walks (16-bit dtypes; float32 reads `attn_mask` only and accepts NULL). */
+ * `attn_mask` as in fa_fwd_peers (its `cols` member is required for 16-bit dtypes). */
 #define FA_BWD_DKDV 1
 #define FA_BWD_DQ 2
 #define FA_BWD_FUSED 4
@@ -114,8 +128,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
-                   const uint8_t* attn_mask, const int64_t attn_mask_strides[3], const uint8_t* attn_mask_t,
-                   const int64_t attn_mask_t_strides[3], void* stream);
+                   const fa_attn_mask* attn_mask, void* stream);
 
 /* Sequence-parallel (ring) attention helpers — no counterpart in the reference (single GPU); they sit where a caller that
  * shards the SEQUENCE across GPUs combines what fa_fwd / fa_bwd return for one key / value shard at a time.

@@ -1120,3 +1120,34 @@ def test_attention_mask_with_seqlens_and_fp32_dropout():
     mask = torch.rand(2, 1, 200, 200, generator=g) < 0.5
     got = _run_masked(Q, K, V, dO, True, 0.2, mask, None, 0.3, 777)
     _check_masked(Q, K, V, dO, True, 0.2, mask, got, torch.float32, 0.3, 777)
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_mask_block_skipping_long(dtype, D, causal):
+    """Sparse masks over 11 x 11 blocks: most 128 x 128 blocks are empty and skipped (forward tiles whose two halves see
+    different block lists, a leading run of skipped blocks, query / key blocks with nothing visible at all), so the
+    skip paths of every pipeline role run through several ring wrap-arounds."""
+    B, H, N = 1, 2, 1300
+    i = torch.arange(N)
+    band = (i[:, None] - i[None, :]).abs() <= 150                       # sliding window
+    band[300:420] = False                                               # queries that see nothing (most of block 2, 3)
+    band[:, 700:900] = False                                            # keys nobody sees (all of block 6)
+    band[1000:1100, 0:50] = True                                        # a far-away "sink" block for late queries
+    glob = torch.zeros(N, N, dtype=torch.bool)
+    glob[640:768, :] = True                                             # one query block attends everywhere
+    glob[:, 700:900] = False
+    mask = torch.stack([band, band | glob])[None]                       # (1, H, N, N): a different mask per head
+    scale = 1.0 / math.sqrt(D)
+    Q, K, V, dO = make_inputs(95, B, H, N, D, dtype)
+    got = _run_masked(Q, K, V, dO, causal, scale, mask)
+    _check_masked(Q, K, V, dO, causal, scale, mask, got, dtype)
+    # the block summary must not change any value: same run with skipping disabled
+    from flash_attention_dlrs_b200 import AttentionMask
+    am = AttentionMask(mask.to(DEV))
+    am.blocks.fill_(1)
+    q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
+    O2, L2 = flash_attention_forward(q, k, v, DEV, causal, scale, None, 0.0, None, am)
+    g2 = flash_attention_backward(q, k, v, O2, do, L2, DEV, True, causal, scale, None, 0.0, None, am)
+    for a, b in zip(got, (O2, L2, *g2)):
+        assert torch.equal(a, b.cpu())

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 5
+    assert lib.fa_version() == 6
     assert isinstance(lib.fa_last_error(), bytes)
 
 
@@ -233,24 +233,48 @@ def test_c_abi_rejects_bad_dropout_arguments():
     null = ctypes.c_void_p(0)
     peers = (ctypes.c_void_p * 1)()
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 1.0, 0,
-                          null, None, null)
+                          None, null)
     assert rc < 0 and b"dropout_p" in lib.fa_last_error()
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 128, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.5, 0,
-                          null, None, null)
+                          None, null)
     assert rc < 0 and b"FP8" in lib.fa_last_error()
     rc = lib.fa_bwd_partial(null, null, null, null, null, null, null, null, null, null, 0, 1, 1, 128, 64, s, s, s, s, s, s, s,
-                            1, 1.0, 0, 4, null, 0.5, 0, null, None, null, None, null)
+                            1, 1.0, 0, 4, null, 0.5, 0, None, null)
     assert rc < 0 and b"FA_BWD_FUSED" in lib.fa_last_error()
-    # attention mask: row pitch must cover N rounded up to 128 and keep 16-byte groups aligned
-    ms = (ctypes.c_int64 * 3)(0, 0, 100)
-    fake = ctypes.c_void_p(4096)
+    # attention mask (fa_attn_mask): row pitch must cover N rounded up to 128 and keep 16-byte groups aligned
+    am = _lib.AttnMaskStruct()
+    am.rows = 4096
+    am.rows_strides = (ctypes.c_int64 * 3)(0, 0, 100)
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 0.0, 0,
-                          fake, ms, null)
+                          ctypes.byref(am), null)
     assert rc < 0 and b"row pitch" in lib.fa_last_error()
-    ms = (ctypes.c_int64 * 3)(0, 0, 128)
+    am.rows_strides = (ctypes.c_int64 * 3)(0, 0, 128)
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.0, 0,
-                          fake, ms, null)
+                          ctypes.byref(am), null)
     assert rc < 0 and b"FP8" in lib.fa_last_error()
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 0.5, 1,
-                          fake, ms, null)
+                          ctypes.byref(am), null)
     assert rc < 0 and b"float32 only" in lib.fa_last_error()
+    rc = lib.fa_bwd_partial(null, null, null, null, null, null, null, null, null, null, 0, 1, 1, 100, 64, s, s, s, s, s, s, s,
+                            1, 1.0, 0, 3, null, 0.0, 0, ctypes.byref(am), null)
+    assert rc < 0 and b"cols" in lib.fa_last_error()
+
+
+def test_attention_mask_packing_on_cpu():
+    """AttentionMask: padded row pitch, transposed copy and 128 x 128 block summary (pure torch, no GPU needed)."""
+    N = 300
+    m = torch.zeros(2, 1, N, N, dtype=torch.bool)
+    m[0, 0, 5, 290] = True        # block (0, 2)
+    m[1, 0, 200, 130] = True      # block (1, 1)
+    am = _native.AttentionMask(m)
+    assert am.rows.shape == (2, 1, N, 384) and am.rows.stride(-2) == 384
+    assert am.rows[0, 0, 5, 290] == 1 and am.cols[0, 0, 290, 5] == 1 and am.rows.sum() == 2 and am.cols.sum() == 2
+    want = torch.zeros(2, 1, 3, 3, dtype=torch.uint8)
+    want[0, 0, 0, 2] = 1
+    want[1, 0, 1, 1] = 1
+    assert torch.equal(am.blocks, want)
+    st = am.struct(2, 4, N, torch.device("cpu"))
+    assert st.rows_strides[1] == 0 and st.rows_strides[2] == 384 and st.blocks_strides[2] == 3
+    with pytest.raises(ValueError):
+        am.struct(3, 4, N, torch.device("cpu"))
+    assert _native.AttentionMask(torch.ones(N, N)).shape == (1, 1, N)

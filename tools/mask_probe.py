@@ -31,7 +31,11 @@ def t(fn, reps=20):
 flops = 4.0 * B * H * N * N * D
 masks = {"none": None,
          "random 90% (N,N)": AttentionMask(torch.rand(N, N, device=dev) < 0.9),
-         "random 90% (B,H,N,N)": AttentionMask(torch.rand(B, H, N, N, device=dev) < 0.9)}
+         "random 90% (B,H,N,N)": AttentionMask(torch.rand(B, H, N, N, device=dev) < 0.9),
+         "sliding window +-512 (N,N)": AttentionMask((torch.arange(N, device=dev)[:, None]
+                                                      - torch.arange(N, device=dev)[None, :]).abs() <= 512),
+         "block-sparse 25% (N,N)": AttentionMask((torch.rand(N // 128, N // 128, device=dev) < 0.25)
+                                                 .repeat_interleave(128, 0).repeat_interleave(128, 1))}
 for name, am in masks.items():
     kw = dict(attn_mask=am)
     O, L = _native.forward(Q, K, V, False, sc, **kw)
@@ -39,5 +43,6 @@ for name, am in masks.items():
     f = t(lambda: _native.forward(Q, K, V, False, sc, **kw))
     dkdv = t(lambda: _native.backward(Q, K, V, O, dO, L, False, sc, 1, delta, **kw))
     dq = t(lambda: _native.backward(Q, K, V, O, dO, L, False, sc, 2, delta, **kw))
-    print(f"mask {name}: fwd {f:.3f} ms ({flops / f / 1e9:.0f} TFLOP/s)  dkdv {dkdv:.3f}  dq {dq:.3f}  "
+    dens = 1.0 if am is None else am.blocks.float().mean().item()
+    print(f"mask {name} (block density {dens:.2f}): fwd {f:.3f} ms ({flops / f / 1e9:.0f} TFLOP/s)  dkdv {dkdv:.3f}  dq {dq:.3f}  "
           f"fwd+bwd {flops * 3.5 / (f + dkdv + dq) / 1e9:.0f} TFLOP/s (dense-equivalent, kernels only)")
