@@ -162,6 +162,8 @@ class AttentionMask:
         if self._struct is None:
             st = _lib.AttnMaskStruct()
             for name, t in (("rows", self.rows), ("cols", self.cols), ("blocks", self.blocks)):
+                if t is None:
+                    continue
                 sB, sH, sN, _ = t.stride()
                 setattr(st, name, t.data_ptr())
                 setattr(st, name + "_strides", _lib._I64x3(0 if Bm == 1 else sB, 0 if Hm == 1 else sH, sN))

@@ -52,8 +52,8 @@ struct BwdParams {
   // mask transposed (made once by the caller), so both read 64 contiguous bytes per thread and half block.
   const uint8_t *amask, *amask_t;
   int64_t am_s[3], amt_s[3];  // {sB, sH, sRow} in bytes
-  // optional block summary [.., query block, key block] (see FwdParams::ablock): flagged-0 blocks are skipped by both
-  // kernels — all barrier traffic stays, the MMAs and the elementwise stage do not run
+  // optional block summary [.., query block, key block] (see FwdParams::ablock): both kernels loop over the blocks
+  // flagged non-zero only (a compacted list built at CTA start), so a skipped block costs nothing
   const uint8_t* ablock;
   int64_t ab_s[3];            // {sB, sH, sI} in bytes
 };
@@ -282,9 +282,9 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ uint64_t in_full[NS], stat_full[NS], in_empty[NS];
   __shared__ uint64_t sc_full[2], p_full[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint8_t s_act[kAmask ? 512 : 4];   // kAmask: block (query block i_begin + it, this key block) has a visible entry
-  __shared__ uint16_t s_ld[kAmask ? 512 : 2];   // kAmask: position of block `it` among the blocks that are not skipped
-  __shared__ int s_any;                         // kAmask: some block of this CTA is not skipped
+  // kAmask with a block summary: the query blocks with something visible for this key block, in order
+  __shared__ uint16_t s_list[kAmask ? 512 : 2];
+  __shared__ int s_nact;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -297,28 +297,21 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_q_total = (nv + 127) >> 7;
   const int i_begin = kCausal ? jb : 0;
   const int n_it = n_q_total - i_begin;
-  const bool use_act = kAmask && p.ablock != nullptr && n_it <= 512;
+  const bool use_list = kAmask && p.ablock != nullptr && n_it <= 512;
   if constexpr (kAmask) {
-    if (threadIdx.x == 0) s_any = use_act ? 0 : 1;
-    if (use_act) {
+    if (use_list && warp == 0) {   // one warp compacts the flags (ballot + prefix count), 32 blocks per step
       const uint8_t* ab = p.ablock + (int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + jb;
-      int any = 0;
-      for (int it = threadIdx.x; it < n_it; it += blockDim.x) any |= (s_act[it] = ab[(int64_t)(i_begin + it) * p.ab_s[2]]);
-      __syncthreads();            // s_any initialised, s_act complete
-      if (any) s_any = 1;         // benign race: every writer stores 1
-      if (threadIdx.x == 0) {
-        int c = 0;
-        for (int it = 0; it < n_it; ++it) {
-          s_ld[it] = s_act[it] ? (uint16_t)c : (uint16_t)0xffff;
-          c += s_act[it] != 0;
-        }
+      int c = 0;
+      for (int base = 0; base < n_it; base += 32) {
+        const int it = base + lane;
+        const bool on = it < n_it && ab[(int64_t)(i_begin + it) * p.ab_s[2]] != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, on);
+        if (on) s_list[c + __popc(m & ((1u << lane) - 1u))] = (uint16_t)it;
+        c += __popc(m);
       }
+      if (lane == 0) s_nact = c;
     }
   }
-  // (published by the __syncthreads below)  Skipped blocks are not loaded: the Q / dO / statistics ring is indexed by the
-  // position among the blocks that are not skipped; the score / P barriers keep one phase per block.
-  auto active = [&](int it) -> bool { return !use_act || s_act[it] != 0; };
-  auto ring_index = [&](int it) -> int { return use_act ? (int)s_ld[it] : it; };
 
   if (threadIdx.x == 0) {
     mbar_init(&kv_full, 1);
@@ -345,6 +338,10 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // every role walks the same list: step k handles query block i_begin + block_of(k); ring stages and barrier phases
+  // are functions of k, so the pipeline protocol is exactly the dense one over a shorter sequence
+  const int n_loop = use_list ? s_nact : n_it;
+  auto block_of = [&](int k) -> int { return use_list ? (int)s_list[k] : k; };
 
   if (warp >= 8) {
   setmaxnreg_dec<72>();
@@ -359,11 +356,10 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     const float* lsep = p.lse + ((int64_t)b * p.H + h) * p.N;
     const float* dlp = p.delta + ((int64_t)b * p.H + h) * p.N;
-    for (int it = 0; it < n_it; ++it) {
-      if (kAmask && !active(it)) continue;
-      const int idx = kAmask ? ring_index(it) : it;
-      const int s = idx % NS;
-      const uint32_t ph = (idx / NS) & 1;
+    for (int k = 0; k < n_loop; ++k) {
+      const int it = kAmask ? block_of(k) : k;
+      const int s = k % NS;
+      const uint32_t ph = (k / NS) & 1;
       const int q0 = (i_begin + it) * 128;
       mbar_wait(&in_empty[s], ph ^ 1);
       if (lane == 0) {
@@ -397,21 +393,19 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t do_mn = umma_lo_mnmajor(smem_u32(sDO), Cfg::kBoxBytes);
 
       // S^T half = K_j Q_i[half]^T ; dP^T half = V_j dO_i[half]^T
-      auto issue_score = [&](int half, int s, bool act) {
+      auto issue_score = [&](int half, int s) {
         const uint32_t bq = q_lo + s * kTileLo + half * kHalfLo, bdo = do_lo + s * kTileLo + half * kHalfLo;
         const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
-        if (act) {
-          static_for<0, kD / 16>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
-            umma_ss_off<off, off>(dS, k_lo, bq, idesc_sc, k > 0);
-          });
-          static_for<0, kD / 16>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
-            umma_ss_off<off, off>(dDP, v_lo, bdo, idesc_sc, k > 0);
-          });
-        }
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+          umma_ss_off<off, off>(dS, k_lo, bq, idesc_sc, k > 0);
+        });
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+          umma_ss_off<off, off>(dDP, v_lo, bdo, idesc_sc, k > 0);
+        });
         tc_commit(&sc_full[half]);
       };
       // dV += P^T[half] dO_i[half] ; dK += dS^T[half] Q_i[half]
@@ -431,34 +425,28 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       };
 
       mbar_wait(&kv_full, 0);
-      if (!kAmask || active(0)) mbar_wait(&in_full[0], 0);
-      tc_fence_after();
-      issue_score(0, 0, !kAmask || active(0));
-      issue_score(1, 0, !kAmask || active(0));
-      bool acc_started = false;   // kAmask: the first block that is not skipped initialises dK / dV
-      for (int it = 0; it < n_it; ++it) {
-        const bool more = it + 1 < n_it;
-        const bool act = !kAmask || active(it), act_n = !kAmask || (more && active(it + 1));
-        const int idx = kAmask ? ring_index(it) : it, idx_n = (kAmask && more) ? ring_index(it + 1) : it + 1;
-        const int s = idx % NS, sn = idx_n % NS;   // (meaningful only for blocks that are not skipped)
+      if (!kAmask || n_loop > 0) {
+        mbar_wait(&in_full[0], 0);
+        tc_fence_after();
+        issue_score(0, 0);
+        issue_score(1, 0);
+      }
+      for (int it = 0; it < n_loop; ++it) {   // (`it` counts list steps here: only stages and phases depend on it)
+        const int s = it % NS, sn = (it + 1) % NS;
+        const bool more = it + 1 < n_loop;
         mbar_wait(&p_full[0], it & 1);
         tc_fence_after();
-        if (act) issue_grad(0, s, kAmask ? !acc_started : it == 0);
+        issue_grad(0, s, it == 0);
         if (more) {
-          if (act_n) {
-            mbar_wait(&in_full[sn], (idx_n / NS) & 1);
-            tc_fence_after();
-          }
-          issue_score(0, sn, act_n);
+          mbar_wait(&in_full[sn], ((it + 1) / NS) & 1);
+          tc_fence_after();
+          issue_score(0, sn);
         }
         mbar_wait(&p_full[1], it & 1);
         tc_fence_after();
-        if (act) {
-          issue_grad(1, s, false);
-          acc_started = true;
-          tc_commit(&in_empty[s]);
-        }
-        if (more) issue_score(1, sn, act_n);
+        issue_grad(1, s, false);
+        tc_commit(&in_empty[s]);
+        if (more) issue_score(1, sn);
       }
       tc_commit(&acc_full);
     }
@@ -484,21 +472,13 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if constexpr (kAmask)
       amt_row = p.amask_t + (int64_t)b * p.amt_s[0] + (int64_t)h * p.amt_s[1] + (int64_t)min(k0 + row, p.N - 1) * p.amt_s[2];
 
-    for (int it = 0; it < n_it; ++it) {
-      const int idx = kAmask ? ring_index(it) : it;
-      const int s = idx % NS;
+    for (int k = 0; k < n_loop; ++k) {
+      const int it = kAmask ? block_of(k) : k;
+      const int s = k % NS;
       uint32_t mk[16] = {};
-      if constexpr (kAmask) {
-        if (!active(it)) {   // skipped block: keep the score / P barrier protocol, do no work
-          mbar_wait(&sc_full[half], it & 1);
-          tc_fence_before();
-          mbar_arrive(&p_full[half]);
-          continue;
-        }
-        amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64);
-      }
-      mbar_wait(&stat_full[s], (idx / NS) & 1);
-      mbar_wait(&sc_full[half], it & 1);
+      if constexpr (kAmask) amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64);
+      mbar_wait(&stat_full[s], (k / NS) & 1);
+      mbar_wait(&sc_full[half], k & 1);
       tc_fence_after();
       const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
@@ -521,10 +501,10 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (half == 0) {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dv) + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)kv_row * p.dv_s[2];
       store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base, kD, kDrop ? p.drop.rp : 1.0f, dst, in_range,
-                            !kAmask || s_any != 0);
+                            !kAmask || n_loop > 0);
     } else {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dk) + b * p.dk_s[0] + h * p.dk_s[1] + (int64_t)kv_row * p.dk_s[2];
-      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc1 + lane_base, kD, p.scale, dst, in_range, !kAmask || s_any != 0);
+      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc1 + lane_base, kD, p.scale, dst, in_range, !kAmask || n_loop > 0);
     }
   }
 
@@ -552,9 +532,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __shared__ uint64_t k_full[NK], k_empty[NK], v_full[NV], v_empty[NV];
   __shared__ uint64_t sc_full[2], sc_free[2], p_full[2], ds_free[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint8_t s_act[kAmask ? 512 : 4];   // kAmask: block (this query block, key block it) has a visible entry
-  __shared__ uint16_t s_ld[kAmask ? 512 : 2];   // kAmask: position of key block `it` among the blocks that are not skipped
-  __shared__ int s_any;                         // kAmask: some block of this CTA is not skipped
+  // kAmask with a block summary: the key blocks with something visible for this query block, in order
+  __shared__ uint16_t s_list[kAmask ? 512 : 2];
+  __shared__ int s_nact;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -569,28 +549,21 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // Non-causal: keys >= nv in the last key block are masked explicitly (padded K rows are real data, not TMA zero fill);
   // causal: the diagonal mask of the last block already removes them (valid rows are < nv).
   const bool tail_mask = !kCausal && (nv & 127) != 0;
-  const bool use_act = kAmask && p.ablock != nullptr && n_it <= 512;
+  const bool use_list = kAmask && p.ablock != nullptr && n_it <= 512;
   if constexpr (kAmask) {
-    if (threadIdx.x == 0) s_any = use_act ? 0 : 1;
-    if (use_act) {
+    if (use_list && warp == 0) {   // one warp compacts the flags (ballot + prefix count), 32 blocks per step
       const uint8_t* ab = p.ablock + (int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)ib * p.ab_s[2];
-      int any = 0;
-      for (int it = threadIdx.x; it < n_it; it += blockDim.x) any |= (s_act[it] = ab[it]);
-      __syncthreads();            // s_any initialised, s_act complete
-      if (any) s_any = 1;         // benign race: every writer stores 1
-      if (threadIdx.x == 0) {
-        int c = 0;
-        for (int it = 0; it < n_it; ++it) {
-          s_ld[it] = s_act[it] ? (uint16_t)c : (uint16_t)0xffff;
-          c += s_act[it] != 0;
-        }
+      int c = 0;
+      for (int base = 0; base < n_it; base += 32) {
+        const int it = base + lane;
+        const bool on = it < n_it && ab[it] != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, on);
+        if (on) s_list[c + __popc(m & ((1u << lane) - 1u))] = (uint16_t)it;
+        c += __popc(m);
       }
+      if (lane == 0) s_nact = c;
     }
   }
-  // (published by the __syncthreads below)  Skipped key blocks are not loaded: the K and V rings are indexed by the
-  // position among the blocks that are not skipped; the score / dS barriers keep one phase per block.
-  auto active = [&](int it) -> bool { return !use_act || s_act[it] != 0; };
-  auto ring_index = [&](int it) -> int { return use_act ? (int)s_ld[it] : it; };
 
   if (threadIdx.x == 0) {
     mbar_init(&qdo_full, 1);
@@ -623,6 +596,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // every role walks the same list: step k handles key block block_of(k); ring stages and barrier phases are functions
+  // of k, so the pipeline protocol is exactly the dense one over a shorter sequence
+  const int n_loop = use_list ? s_nact : n_it;
+  auto block_of = [&](int k) -> int { return use_list ? (int)s_list[k] : k; };
 
   if (warp >= 8) {
   setmaxnreg_dec<72>();
@@ -634,18 +611,17 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_4d(sQ + bx * Cfg::kBoxBytes, &tmQ, &qdo_full, bx * 64, q0, h, b);
         tma_load_4d(sDO + bx * Cfg::kBoxBytes, &tmDO, &qdo_full, bx * 64, q0, h, b);
       }
-      for (int it = 0; it < n_it; ++it) {
-        if (kAmask && !active(it)) continue;
-        const int idx = kAmask ? ring_index(it) : it;
-        const int sk = idx % NK, sv = idx % NV;
-        mbar_wait(&k_empty[sk], ((idx / NK) & 1) ^ 1);
+      for (int k = 0; k < n_loop; ++k) {
+        const int kv0 = (kAmask ? block_of(k) : k) * 128;
+        const int sk = k % NK, sv = k % NV;
+        mbar_wait(&k_empty[sk], ((k / NK) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[sk], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
-          tma_load_4d(sK + sk * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &k_full[sk], bx * 64, it * 128, h, b);
-        mbar_wait(&v_empty[sv], ((idx / NV) & 1) ^ 1);
+          tma_load_4d(sK + sk * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmK, &k_full[sk], bx * 64, kv0, h, b);
+        mbar_wait(&v_empty[sv], ((k / NV) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[sv], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
-          tma_load_4d(sV + sv * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &v_full[sv], bx * 64, it * 128, h, b);
+          tma_load_4d(sV + sv * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmV, &v_full[sv], bx * 64, kv0, h, b);
       }
     }
     __syncwarp();
@@ -659,20 +635,18 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t k_mn = umma_lo_mnmajor(smem_u32(sK), Cfg::kBoxBytes);
 
       // S half = Q_i K_j[half]^T ; dP half = dO_i V_j[half]^T      (A operands resident in TMEM)
-      auto issue_score = [&](int half, int sk, int sv, bool act) {
+      auto issue_score = [&](int half, int sk, int sv) {
         const uint32_t bk = k_lo + sk * kTileLo + half * kHalfLo, bv = v_lo + sv * kTileLo + half * kHalfLo;
         const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
         const uint32_t aQ = tmem + Cfg::kTmemQA, aDO = tmem + Cfg::kTmemDOA;
-        if (act) {
-          static_for<0, kD / 16>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            umma_ts_off<k * 8, umma_koff_kmajor(k, Cfg::kBoxBytes)>(dS, aQ, bk, idesc_sc, k > 0);
-          });
-          static_for<0, kD / 16>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            umma_ts_off<k * 8, umma_koff_kmajor(k, Cfg::kBoxBytes)>(dDP, aDO, bv, idesc_sc, k > 0);
-          });
-        }
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ts_off<k * 8, umma_koff_kmajor(k, Cfg::kBoxBytes)>(dS, aQ, bk, idesc_sc, k > 0);
+        });
+        static_for<0, kD / 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ts_off<k * 8, umma_koff_kmajor(k, Cfg::kBoxBytes)>(dDP, aDO, bv, idesc_sc, k > 0);
+        });
         tc_commit(&sc_full[half]);
       };
       // dQ += dS[half] K_j[half]
@@ -680,65 +654,54 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // first box of the Q_i staging tile, sdS[b] the first box of the dO_i staging tile (both dead after the TMEM copy).
       const uint32_t ds_lo[2] = {umma_lo_kmajor(smem_u32(sQ)), umma_lo_kmajor(smem_u32(sDO))};
       constexpr uint32_t idesc_gs = umma_idesc_f16(kBf16, 128, kD, 0, 1);
-      auto issue_grad = [&](int half, int s, bool first, bool act) {
+      auto issue_grad = [&](int half, int s, bool first) {
         const uint32_t bk = k_mn + s * kTileLo + half * umma_koff_mnmajor(4);
         const uint32_t dQ_t = tmem + Cfg::kTmemAcc0, aDS = ds_lo[half];
-        if (act) {
-          static_for<0, 4>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            umma_ss_off<umma_koff_kmajor(k, Cfg::kBoxBytes), umma_koff_mnmajor(k)>(dQ_t, aDS, bk, idesc_gs,
-                                                                                  !(first && k == 0));
-          });
-        }
+        static_for<0, 4>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          umma_ss_off<umma_koff_kmajor(k, Cfg::kBoxBytes), umma_koff_mnmajor(k)>(dQ_t, aDS, bk, idesc_gs,
+                                                                                !(first && k == 0));
+        });
         tc_commit(&ds_free[half]);
       };
 
       mbar_wait(&qdo_tmem, 0);
-      const bool act0 = !kAmask || active(0);
-      if (act0) {
+      if (!kAmask || n_loop > 0) {
         mbar_wait(&k_full[0], 0);
         mbar_wait(&v_full[0], 0);
+        tc_fence_after();
+        issue_score(0, 0, 0);
+        issue_score(1, 0, 0);
+        tc_commit(&v_empty[0]);
       }
-      tc_fence_after();
-      issue_score(0, 0, 0, act0);
-      issue_score(1, 0, 0, act0);
-      if (act0) tc_commit(&v_empty[0]);
-      bool acc_started = false;   // kAmask: the first block that is not skipped initialises dQ
-      for (int it = 0; it < n_it; ++it) {
-        const bool more = it + 1 < n_it;
-        const bool act = !kAmask || active(it), act_n = !kAmask || (more && active(it + 1));
-        const int idx = kAmask ? ring_index(it) : it, idx_n = (kAmask && more) ? ring_index(it + 1) : it + 1;
-        const int sk = idx % NK, skn = idx_n % NK, svn = idx_n % NV;   // (meaningful only for blocks that are not skipped)
+      for (int it = 0; it < n_loop; ++it) {   // (`it` counts list steps here: only stages and phases depend on it)
+        const int sk = it % NK, skn = (it + 1) % NK, svn = (it + 1) % NV;
+        const bool more = it + 1 < n_loop;
         // the score accumulators are free as soon as the elementwise warps hold them in registers: the next
         // scores run on the tensor core while dS is being computed
         fa_trace(0, it, 0);
         if (more) {
           mbar_wait(&sc_free[0], it & 1);
-          if (act_n) {
-            mbar_wait(&k_full[skn], (idx_n / NK) & 1);
-            mbar_wait(&v_full[svn], (idx_n / NV) & 1);
-          }
+          mbar_wait(&k_full[skn], ((it + 1) / NK) & 1);
+          mbar_wait(&v_full[svn], ((it + 1) / NV) & 1);
           tc_fence_after();
-          issue_score(0, skn, svn, act_n);
+          issue_score(0, skn, svn);
           fa_trace(0, it, 1);
           mbar_wait(&sc_free[1], it & 1);
           tc_fence_after();
-          issue_score(1, skn, svn, act_n);
-          if (act_n) tc_commit(&v_empty[svn]);
+          issue_score(1, skn, svn);
+          tc_commit(&v_empty[svn]);
         }
         fa_trace(0, it, 2);
         mbar_wait(&p_full[0], it & 1);
         fa_trace(0, it, 3);
         tc_fence_after();
-        issue_grad(0, sk, kAmask ? !acc_started : it == 0, act);
+        issue_grad(0, sk, it == 0);
         mbar_wait(&p_full[1], it & 1);
         fa_trace(0, it, 4);
         tc_fence_after();
-        issue_grad(1, sk, false, act);
-        if (act) {
-          acc_started = true;
-          tc_commit(&k_empty[sk]);
-        }
+        issue_grad(1, sk, false);
+        tc_commit(&k_empty[sk]);
         fa_trace(0, it, 5);
       }
       tc_commit(&acc_full);
@@ -796,21 +759,12 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
 
     const uint32_t sds = smem_u32(half == 0 ? sQ : sDO);   // this half's dS box (see the MMA warp)
-    for (int it = 0; it < n_it; ++it) {
+    for (int k = 0; k < n_loop; ++k) {
+      const int it = kAmask ? block_of(k) : k;   // key block of this step
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 0);   // about to wait for scores
       uint32_t mk[16] = {};
-      if constexpr (kAmask) {
-        if (!active(it)) {   // skipped block: keep the barrier protocol, do no work
-          mbar_wait(&sc_full[half], it & 1);
-          tc_fence_before();
-          mbar_arrive(&sc_free[half]);
-          if (it > 0) mbar_wait(&ds_free[half], (it - 1) & 1);
-          mbar_arrive(&p_full[half]);
-          continue;
-        }
-        amask_load64(mk, am_row + it * 128 + half * 64);
-      }
-      mbar_wait(&sc_full[half], it & 1);
+      if constexpr (kAmask) amask_load64(mk, am_row + it * 128 + half * 64);
+      mbar_wait(&sc_full[half], k & 1);
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();
       uint32_t pd[32];
@@ -824,7 +778,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       else
         dq_elementwise_half<kBf16, false, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
                                                          drop_shift, p.drop.thresh, p.drop.rp, mk);
-      if (it > 0) mbar_wait(&ds_free[half], (it - 1) & 1);        // dQ MMAs of the previous block have read the box
+      if (k > 0) mbar_wait(&ds_free[half], (k - 1) & 1);          // dQ MMAs of the previous block have read the box
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, ch)), "r"(pd[ch * 4]),
@@ -841,7 +795,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint16_t* dst = reinterpret_cast<uint16_t*>(p.dq) + b * p.dq_s[0] + h * p.dq_s[1] + (int64_t)q_row * p.dq_s[2] +
                     half * (kD / 2);
     store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base + half * (kD / 2), kD / 2, p.scale, dst, in_range,
-                          !kAmask || s_any != 0);
+                          !kAmask || n_loop > 0);
   }
 
   tc_fence_before();

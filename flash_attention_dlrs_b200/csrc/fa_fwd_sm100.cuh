@@ -65,10 +65,10 @@ struct FwdParams {
   const uint8_t* amask;
   int64_t am_sB, am_sH, am_sN;
   // Optional block summary of the mask: ablock[.., i, j] != 0 iff some (query, key) of the 128 x 128 block (i, j) is
-  // visible.  Blocks flagged 0 are skipped: the S / P / O barriers keep their per-block traffic (so that part of the
-  // protocol is the one of the dense kernel) but no MMAs are issued and no softmax work is done for them, and a key block
-  // that neither query tile of the CTA needs is not loaded at all (the K / V ring is indexed by the count of loaded
-  // blocks).  nullptr, or more than 512 key blocks: no skipping.
+  // visible.  Blocks flagged 0 are skipped: every role of the CTA walks the list of key blocks that at least one of its
+  // two query tiles needs (K / V ring stages and phases count list steps), and a tile touches its S / P / O barriers only
+  // for its own visible blocks (phases count those) — a skipped block costs nothing.  nullptr, or more than 512 key
+  // blocks: no skipping.
   const uint8_t* ablock;
   int64_t ab_sB, ab_sH, ab_sI;
 };
@@ -114,7 +114,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __shared__ uint64_t k_full[NS], k_empty[NS], v_full[NS], v_empty[NS];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint8_t s_act[2][kAmask ? 512 : 4];   // kAmask: block (tile t, key block j) has a visible entry
-  __shared__ uint16_t s_ld[kAmask ? 512 : 2];      // kAmask: position of key block j among the loaded blocks (0xffff: not loaded)
+  __shared__ uint16_t s_list[kAmask ? 512 : 2];    // kAmask: the key blocks some tile of this CTA needs, in order
+  __shared__ int s_nlist;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,19 +143,21 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int j = threadIdx.x; j < nkv[t]; j += blockDim.x) s_act[t][j] = ab[j];
       }
       __syncthreads();   // (use_act is uniform over the CTA)
-      if (threadIdx.x == 0) {
+      if (warp == 0) {   // one warp compacts the union of the two tiles' flags (ballot + prefix count), 32 blocks per step
         int c = 0;
-        for (int j = 0; j < nkv_max; ++j) {
-          const bool ld = (j < nkv[0] && s_act[0][j]) || (j < nkv[1] && s_act[1][j]);
-          s_ld[j] = ld ? (uint16_t)c : (uint16_t)0xffff;
-          c += ld;
+        for (int base = 0; base < nkv_max; base += 32) {
+          const int j = base + lane;
+          const bool on = (j < nkv[0] && s_act[0][j]) || (j < nkv[1] && s_act[1][j]);
+          const uint32_t m = __ballot_sync(0xffffffffu, on);
+          if (on) s_list[c + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+          c += __popc(m);
         }
+        if (lane == 0) s_nlist = c;
       }
     }
   }
-  // (both published by the __syncthreads below)
+  // (published by the __syncthreads below)
   auto active = [&](int t, int j) -> bool { return !use_act || s_act[t][j] != 0; };
-  auto load_index = [&](int j) -> int { return use_act ? (int)s_ld[j] : j; };   // 0xffff: key block j is not loaded
 
   if (threadIdx.x == 0) {
     for (int t = 0; t < 2; ++t) {
@@ -182,6 +185,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // list step u handles key block block_of(u); without a block summary the list is 0, 1, 2, ...
+  const int n_list = use_act ? s_nlist : nkv_max;
+  auto block_of = [&](int u) -> int { return use_act ? (int)s_list[u] : u; };
 
   if (warp >= 8) {
   setmaxnreg_dec<72>();   // third warpgroup: producer, MMA issuer, two idle warps
@@ -194,11 +200,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tma_load_4d(sQ + t * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmQ, &q_full[t], bx * Cfg::kBoxElems, q0 + 128 * t, h,
                       b);
       }
-      for (int j = 0; j < nkv_max; ++j) {
-        const int idx = kAmask ? load_index(j) : j;
-        if (kAmask && idx == 0xffff) continue;   // no tile of this CTA needs key block j
-        const int s = idx % NS;
-        const uint32_t ph = (idx / NS) & 1;
+      for (int u = 0; u < n_list; ++u) {
+        const int j = kAmask ? block_of(u) : u;
+        const int s = u % NS;
+        const uint32_t ph = (u / NS) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
         for (int bx = 0; bx < Cfg::kBoxes; ++bx)
@@ -221,13 +226,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       auto tS = [&](int t) { return tmem + (t ? Cfg::kTmemS1 : Cfg::kTmemS0); };
       auto tO = [&](int t) { return tmem + (t ? Cfg::kTmemO1 : Cfg::kTmemO0); };
 
-      auto issue_s = [&](int t, int j) {
-        const int idx = kAmask ? load_index(j) : j;
-        const bool loaded = !kAmask || idx != 0xffff;
-        const int s = idx % NS;
+      auto issue_s = [&](int t, int u) {   // S of tile t for list step u (key block j)
+        const int j = kAmask ? block_of(u) : u;
+        const int s = u % NS;
         const uint32_t a0 = qlo + t * kTileLo, b0 = klo + s * kTileLo, d0 = tS(t);
         if (!kAmask || active(t, j)) {
-          mbar_wait(&k_full[s], (idx / NS) & 1);
+          mbar_wait(&k_full[s], (u / NS) & 1);
           tc_fence_after();
           static_for<0, Cfg::kSteps>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
@@ -237,34 +241,34 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             else
               umma_ss_off<off, off>(d0, a0, b0, idesc_s, k > 0);
           });
+          tc_commit(&s_full[t]);
         }
-        tc_commit(&s_full[t]);
         // last tile that reads K block j releases the stage
         const bool last_user = (t == 1) || (nkv[1] <= j);
-        if (last_user && loaded) tc_commit(&k_empty[s]);
+        if (last_user) tc_commit(&k_empty[s]);
       };
 
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(&q_full[t], 0);
-        issue_s(t, 0);
+        if (!kAmask || (n_list > 0 && block_of(0) < nkv[t])) issue_s(t, 0);
       }
-      bool pv_started[2] = {false, false};   // kAmask: the first P.V of a tile that is not skipped initialises O
-      for (int j = 0; j < nkv_max; ++j) {
-        const int idx = kAmask ? load_index(j) : j;
-        const bool loaded = !kAmask || idx != 0xffff;
-        const int s = idx % NS;
+      int n_pv[2] = {0, 0};   // kAmask: P.V products issued per tile so far (barrier phases; the first one initialises O)
+      for (int u = 0; u < n_list; ++u) {
+        const int j = kAmask ? block_of(u) : u;
+        const int jn = (kAmask && u + 1 < n_list) ? block_of(u + 1) : j + 1;   // key block of the next list step
+        const int s = u % NS;
         for (int t = 0; t < ntiles; ++t) {
           if (j >= nkv[t]) continue;
-          if (!kAmask || active(t, j)) mbar_wait(&v_full[s], (idx / NS) & 1);
-          // P arrives in two 64-key halves so the first half of P·V overlaps the second half of the exponentials
-          const uint32_t dO_t = tO(t), aP = tS(t), bV = vlo + s * kTileLo;
-          // 16-bit P: 16 keys = 8 TMEM columns and 2048 bytes of V per MMA; FP8 P: 32 keys = 8 columns and 4096 bytes
-          constexpr int kPSteps = kF8 ? 4 : 8, kVStep = kF8 ? 2 : 1;
-          const bool act = !kAmask || active(t, j);
-          const bool acc0 = kAmask ? pv_started[t] : (j > 0);
-          mbar_wait(&p_full[t][0], j & 1);
-          tc_fence_after();
-          if (act) {
+          if (!kAmask || active(t, j)) {
+            mbar_wait(&v_full[s], (u / NS) & 1);
+            // P arrives in two 64-key halves so the first half of P·V overlaps the second half of the exponentials
+            const uint32_t dO_t = tO(t), aP = tS(t), bV = vlo + s * kTileLo;
+            // 16-bit P: 16 keys = 8 TMEM columns and 2048 bytes of V per MMA; FP8 P: 32 keys = 8 columns and 4096 bytes
+            constexpr int kPSteps = kF8 ? 4 : 8, kVStep = kF8 ? 2 : 1;
+            const int c = kAmask ? n_pv[t] : j;   // this tile's count of visible blocks so far
+            const bool acc0 = c > 0;
+            mbar_wait(&p_full[t][0], c & 1);
+            tc_fence_after();
             static_for<0, kPSteps / 2>([&](auto kc) {
               constexpr int k = decltype(kc)::value;
               if constexpr (kF8)
@@ -272,10 +276,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               else
                 umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, acc0 || (k > 0));
             });
-          }
-          mbar_wait(&p_full[t][1], j & 1);
-          tc_fence_after();
-          if (act) {
+            mbar_wait(&p_full[t][1], c & 1);
+            tc_fence_after();
             static_for<kPSteps / 2, kPSteps>([&](auto kc) {
               constexpr int k = decltype(kc)::value;
               if constexpr (kF8)
@@ -283,12 +285,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               else
                 umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, 1u);
             });
-            pv_started[t] = true;
+            n_pv[t] = c + 1;
+            tc_commit(&o_full[t]);
           }
-          tc_commit(&o_full[t]);
           const bool last_user = (t == 1) || (nkv[1] <= j);
-          if (last_user && loaded) tc_commit(&v_empty[s]);
-          if (j + 1 < nkv[t]) issue_s(t, j + 1);
+          if (last_user) tc_commit(&v_empty[s]);
+          if (kAmask ? (u + 1 < n_list && jn < nkv[t]) : (j + 1 < nkv[t])) issue_s(t, u + 1);
         }
       }
     }
@@ -317,21 +319,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       am_row = p.amask + (int64_t)b * p.am_sB + (int64_t)h * p.am_sH + (int64_t)min(q_row, p.N - 1) * p.am_sN;
 
     float m_used = -INFINITY, l = 0.f;
-    bool seen_block = false;   // kAmask: some key block of this tile was not skipped (O has been written)
-    for (int j = 0; j < my_nkv; ++j) {
+    int n_seen = 0;   // kAmask: key blocks of this tile that were not skipped so far (barrier phases count these)
+    const int n_mine = kAmask ? n_list : my_nkv;
+    for (int u = 0; u < n_mine; ++u) {
+      const int j = kAmask ? block_of(u) : u;
+      if (kAmask && j >= my_nkv) break;
       uint4 mk[kAmask ? 8 : 1];   // this row's 128 mask bytes of key block j, requested before the wait for S
       if constexpr (kAmask) {
-        if (!active(t, j)) {   // skipped block: keep the barrier protocol, do no work
-          mbar_wait(&s_full[t], j & 1);
-          tc_fence_before();
-          mbar_arrive(&p_full[t][0]);
-          mbar_arrive(&p_full[t][1]);
-          continue;
-        }
+        if (!active(t, j)) continue;   // skipped block: nobody touches this tile's barriers for it
 #pragma unroll
         for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
       }
-      mbar_wait(&s_full[t], j & 1);
+      const int c = kAmask ? n_seen : j;
+      mbar_wait(&s_full[t], c & 1);
       tc_fence_after();
 #if FA_ABLATE == 3
       tc_fence_before();
@@ -373,9 +373,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
       }
       const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
-      const bool first_block = kAmask ? !seen_block : (j == 0);
-      seen_block = true;
-      if (first_block) {
+      n_seen = c + 1;
+      if (c == 0) {
         m_used = m_new;
       } else {
         const bool need = (m_new - m_used) * sl2 > 8.0f;
@@ -384,7 +383,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (need) m_used = m_new;
           l *= alpha;
           // O_t is stable once P·V of block j-1 has completed
-          mbar_wait(&o_full[t], (j - 1) & 1);
+          mbar_wait(&o_full[t], (c - 1) & 1);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < kD / 32; ++c) {
@@ -481,7 +480,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
 
     if (my_nkv > 0) {
-      mbar_wait(&o_full[t], (my_nkv - 1) & 1);
+      const int n_done = kAmask ? n_seen : my_nkv;
+      if (n_done > 0) mbar_wait(&o_full[t], (n_done - 1) & 1);
+      // (a tile with every block skipped never waited for anything: its Q load must have landed before the staging
+      // buffer below, which is the Q tile, is overwritten)
+      if (kAmask && n_done == 0) mbar_wait(&q_full[t], 0);
       tc_fence_after();
       float inv_l = (kDrop ? p.drop.rp : 1.0f) / l;   // kept probabilities are scaled by 1 / (1 - p_drop)
       if (kAmask && !(l > 0.f)) inv_l = 0.f;          // no visible key: O = 0 (and L = -inf below)
@@ -497,7 +500,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         uint32_t orr[32];
         tmem_ld_x32(tO + c * 32, orr);
         tc_wait_ld();
-        if (kAmask && !seen_block) {   // every key block of this tile was skipped: O was never written
+        if (kAmask && n_seen == 0) {   // every key block of this tile was skipped: O was never written
 #pragma unroll
           for (int i = 0; i < 32; ++i) orr[i] = 0u;
         }
