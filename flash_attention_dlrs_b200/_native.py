@@ -144,11 +144,13 @@ class AttentionMask:
             return buf
 
         self.rows, self.cols = pack(m), pack(m.transpose(-1, -2))
-        # 128 x 128 block summary: blocks[.., i, j] = some entry of block (i, j) is visible; the kernels skip the others
+        # 128 x 128 block summary: 0 = nothing of block (i, j) is visible (the kernels skip it), 2 = everything is
+        # (its mask bytes are not read), 1 = mixed
         nb = pitch // 128
         sq = torch.zeros((Bm, Hm, pitch, pitch), dtype=torch.bool, device=m.device)
         sq[..., :N, :N] = m
-        self.blocks = sq.view(Bm, Hm, nb, 128, nb, 128).any(-1).any(-2).to(torch.uint8).contiguous()
+        sq = sq.view(Bm, Hm, nb, 128, nb, 128)
+        self.blocks = (sq.any(-1).any(-2).to(torch.uint8) + sq.all(-1).all(-2).to(torch.uint8)).contiguous()
         self.shape = (Bm, Hm, N)
         self._struct = None
 

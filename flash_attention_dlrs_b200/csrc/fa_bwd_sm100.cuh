@@ -53,7 +53,8 @@ struct BwdParams {
   const uint8_t *amask, *amask_t;
   int64_t am_s[3], amt_s[3];  // {sB, sH, sRow} in bytes
   // optional block summary [.., query block, key block] (see FwdParams::ablock): both kernels loop over the blocks
-  // flagged non-zero only (a compacted list built at CTA start), so a skipped block costs nothing
+  // flagged non-zero only (a compacted list built at CTA start), so a skipped block costs nothing; blocks flagged 2
+  // (fully visible) do not load their mask bytes
   const uint8_t* ablock;
   int64_t ab_s[3];            // {sB, sH, sI} in bytes
 };
@@ -62,7 +63,12 @@ struct BwdParams {
 __device__ __forceinline__ bool amask_byte(const uint32_t (&mk)[16], int e) {
   return (mk[e >> 2] & (0xffu << (8 * (e & 3)))) != 0u;
 }
-__device__ __forceinline__ void amask_load64(uint32_t (&mk)[16], const uint8_t* src) {
+__device__ __forceinline__ void amask_load64(uint32_t (&mk)[16], const uint8_t* src, bool full = false) {
+  if (full) {   // block summary says every entry is visible
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mk[i] = 0x01010101u;
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
@@ -476,7 +482,9 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int it = kAmask ? block_of(k) : k;
       const int s = k % NS;
       uint32_t mk[16] = {};
-      if constexpr (kAmask) amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64);
+      if constexpr (kAmask)
+        amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64,
+                     use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)(i_begin + it) * p.ab_s[2] + jb] == 2);
       mbar_wait(&stat_full[s], (k / NS) & 1);
       mbar_wait(&sc_full[half], k & 1);
       tc_fence_after();
@@ -763,7 +771,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int it = kAmask ? block_of(k) : k;   // key block of this step
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 0);   // about to wait for scores
       uint32_t mk[16] = {};
-      if constexpr (kAmask) amask_load64(mk, am_row + it * 128 + half * 64);
+      if constexpr (kAmask)
+        amask_load64(mk, am_row + it * 128 + half * 64,
+                     use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)ib * p.ab_s[2] + it] == 2);
       mbar_wait(&sc_full[half], k & 1);
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();

@@ -65,7 +65,7 @@ struct FwdParams {
   const uint8_t* amask;
   int64_t am_sB, am_sH, am_sN;
   // Optional block summary of the mask: ablock[.., i, j] != 0 iff some (query, key) of the 128 x 128 block (i, j) is
-  // visible.  Blocks flagged 0 are skipped: every role of the CTA walks the list of key blocks that at least one of its
+  // visible; 2 = every entry of the block is visible (its mask bytes are then neither loaded nor applied).  Blocks flagged 0 are skipped: every role of the CTA walks the list of key blocks that at least one of its
   // two query tiles needs (K / V ring stages and phases count list steps), and a tile touches its S / P / O barriers only
   // for its own visible blocks (phases count those) — a skipped block costs nothing.  nullptr, or more than 512 key
   // blocks: no skipping.
@@ -327,8 +327,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       uint4 mk[kAmask ? 8 : 1];   // this row's 128 mask bytes of key block j, requested before the wait for S
       if constexpr (kAmask) {
         if (!active(t, j)) continue;   // skipped block: nobody touches this tile's barriers for it
+      }
+      const bool partial = kAmask && !(use_act && s_act[t][j] == 2);   // some entries of the block are masked out
+      if constexpr (kAmask) {
+        if (partial) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
+          for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
+        }
       }
       const int c = kAmask ? n_seen : j;
       mbar_wait(&s_full[t], c & 1);
@@ -356,7 +361,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int c = 0; c < 128; ++c)
           if (c >= limit) sr[c] = 0xff800000u;         // -inf
       }
-      if constexpr (kAmask) {
+      if (kAmask && partial) {
 #pragma unroll
         for (int c = 0; c < 128; ++c) {
           const uint4& q4 = mk[c >> 4];

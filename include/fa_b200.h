@@ -41,8 +41,9 @@ extern "C" {
  *          to 128 (kernels read whole 16-byte groups of a 128-key block), base 16-byte aligned.
  *   cols   [.., key, query]: the same mask transposed, same layout rules; read by the dK/dV kernel (16-bit dtypes;
  *          float32 reads `rows` only and accepts NULL).  Not used by the forward.
- *   blocks [.., query block, key block] (128 x 128 blocks), optional (NULL = none): 0 = no visible entry in the block.
- *          Such blocks are skipped (no MMAs, no softmax work); with up to 512 blocks per row / column.
+ *   blocks [.., query block, key block] (128 x 128 blocks), optional (NULL = none): 0 = no visible entry in the block
+ *          (such blocks are skipped: not loaded, no MMAs, no softmax work), 2 = every entry visible (`rows` / `cols` are
+ *          not read for it), 1 = mixed.  Up to 512 blocks per row / column.
  * A query with no visible key gets O = 0, lse = -inf and contributes nothing to the gradients. */
 typedef struct fa_attn_mask {
   const uint8_t* rows;

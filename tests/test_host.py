@@ -278,3 +278,6 @@ def test_attention_mask_packing_on_cpu():
     with pytest.raises(ValueError):
         am.struct(3, 4, N, torch.device("cpu"))
     assert _native.AttentionMask(torch.ones(N, N)).shape == (1, 1, N)
+    full = _native.AttentionMask(torch.ones(256, 256, dtype=torch.bool).tril())
+    assert full.blocks.flatten().tolist() == [1, 0, 2, 1]   # diagonal blocks mixed, lower block fully visible, upper empty
+    assert _native.AttentionMask(torch.ones(N, N)).blocks[0, 0].tolist() == [[2, 2, 1], [2, 2, 1], [1, 1, 1]]   # ragged edge

@@ -36,4 +36,4 @@ for w in (0, 128, 512, 1024, 2048, 4096, 8192):
     f = t(lambda: _native.forward(Q, K, V, False, sc, **kw))
     dkdv = t(lambda: _native.backward(Q, K, V, O, dO, L, False, sc, 1, delta, **kw))
     dq = t(lambda: _native.backward(Q, K, V, O, dO, L, False, sc, 2, delta, **kw))
-    print(f"window +-{w}: block density {am.blocks.float().mean().item():.3f}  fwd {f:.3f} ms  dkdv {dkdv:.3f}  dq {dq:.3f}")
+    print(f"window +-{w}: block density {(am.blocks > 0).float().mean().item():.3f}  fwd {f:.3f} ms  dkdv {dkdv:.3f}  dq {dq:.3f}")

@@ -43,6 +43,6 @@ for name, am in masks.items():
     f = t(lambda: _native.forward(Q, K, V, False, sc, **kw))
     dkdv = t(lambda: _native.backward(Q, K, V, O, dO, L, False, sc, 1, delta, **kw))
     dq = t(lambda: _native.backward(Q, K, V, O, dO, L, False, sc, 2, delta, **kw))
-    dens = 1.0 if am is None else am.blocks.float().mean().item()
+    dens = 1.0 if am is None else (am.blocks > 0).float().mean().item()
     print(f"mask {name} (block density {dens:.2f}): fwd {f:.3f} ms ({flops / f / 1e9:.0f} TFLOP/s)  dkdv {dkdv:.3f}  dq {dq:.3f}  "
           f"fwd+bwd {flops * 3.5 / (f + dkdv + dq) / 1e9:.0f} TFLOP/s (dense-equivalent, kernels only)")
