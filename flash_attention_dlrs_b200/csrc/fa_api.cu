@@ -110,6 +110,7 @@ int launch_fwd16(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
                  int B, cudaStream_t st) {
   using Cfg = fa::FwdCfg<kD, kElt>;
   if constexpr (kElt < 3 && !kDrop && !kAmask) {
+    if (p.drop.thresh && p.amask) return launch_fwd16<kElt, kD, kCausal, true, true>(tq, tk, tv, p, H, B, st);
     if (p.drop.thresh) return launch_fwd16<kElt, kD, kCausal, true, false>(tq, tk, tv, p, H, B, st);
     if (p.amask) return launch_fwd16<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
   }
@@ -159,6 +160,7 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
 template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaStream_t st) {
   if constexpr (!kDrop && !kAmask) {
+    if (p.drop.thresh && p.amask) return launch_bwd16<kBf16, kD, kCausal, true, true>(m, p, which, st);
     if (p.drop.thresh) return launch_bwd16<kBf16, kD, kCausal, true, false>(m, p, which, st);
     if (p.amask) return launch_bwd16<kBf16, kD, kCausal, false, true>(m, p, which, st);
   }
@@ -264,8 +266,6 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   if (int r = make_drop("fa_fwd_peers", dropout_p, dropout_seed, &drop)) return r;
   if (drop.thresh && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
     return fail(-13, "fa_fwd_peers: dropout is not implemented for the FP8 forward");
-  if (drop.thresh && attn_mask && dtype != FA_DTYPE_F32)
-    return fail(-14, "fa_fwd_peers: dropout together with an attention mask is implemented for float32 only");
   if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_o)) return fail(-12, "fa_fwd_peers: 0 <= n_peers <= 7 and peer_o non-null");
   if (n_peers > 0 && dtype == FA_DTYPE_F32) return fail(-12, "fa_fwd_peers: peer copies are implemented for the 16-bit and FP8 kernels");
   for (int i = 0; i < n_peers; ++i)
@@ -419,8 +419,6 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   if (int r = make_drop("fa_bwd_partial", dropout_p, dropout_seed, &drop)) return r;
   if (drop.thresh && which == FA_BWD_FUSED)
     return fail(-13, "fa_bwd_partial: FA_BWD_FUSED has no dropout; use the two-kernel path");
-  if (drop.thresh && attn_mask && dtype != FA_DTYPE_F32)
-    return fail(-14, "fa_bwd_partial: dropout together with an attention mask is implemented for float32 only");
   if (which != FA_BWD_FUSED && ((which & (FA_BWD_DKDV | FA_BWD_DQ)) == 0 || (which & ~(FA_BWD_DKDV | FA_BWD_DQ))))
     return fail(-10, "fa_bwd_partial: which must be FA_BWD_FUSED or a non-empty subset of FA_BWD_DKDV | FA_BWD_DQ");
   if (which == FA_BWD_FUSED) {

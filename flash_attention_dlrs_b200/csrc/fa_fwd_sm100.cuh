@@ -102,7 +102,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   constexpr bool kF8 = Cfg::kF8, kBf16 = kElt == 1, kE5M2 = kElt == 4;
   static_assert(!kF8 || kD == 128, "the FP8 forward runs at D = 128 (one 128-byte box per row); pad in the caller");
   static_assert(!(kF8 && (kDrop || kAmask)), "dropout and attention masks are implemented for the 16-bit kernels");
-  static_assert(!(kDrop && kAmask), "dropout and an attention mask are separate instantiations");
   constexpr int NS = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

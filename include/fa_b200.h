@@ -80,8 +80,7 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
  * and kept entries are scaled by 1 / (1 - that); lse stays the logsumexp of the undropped scores.  The keep mask is a
  * pure function of (dropout_seed, b, h, query, key), restated by the oracle (oracle/attention_oracle.py:
  * dropout_keep_mask); fa_bwd_partial regenerates it from the same (dropout_p, dropout_seed).
- * `attn_mask` (NULL = none): an arbitrary attention mask, see fa_attn_mask above.  float16 / bfloat16 / float32; with
- * dropout at the same time: float32 only. */
+ * `attn_mask` (NULL = none): an arbitrary attention mask, see fa_attn_mask above.  float16 / bfloat16 / float32. */
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,

@@ -948,8 +948,8 @@ def test_dropout_autograd_seeding_and_determinism():
 @pytest.mark.parametrize("case", range(40))
 def test_randomized_feature_combinations(case):
     """Seeded random draws over everything the default path takes at once — dtype, head size (padded or not), ragged N,
-    causal, scale, per-batch lengths, dropout, an arbitrary mask (16-bit: not together with dropout) — against the
-    float64 closed form evaluated per batch element."""
+    causal, scale, per-batch lengths, dropout, an arbitrary mask — against the float64 closed form evaluated per batch
+    element."""
     rng = np.random.default_rng(1000 + case)
     dtype = (torch.bfloat16, torch.float16, torch.float32)[case % 3]
     d = int(rng.choice([16, 24, 40, 64, 72, 128]))
@@ -961,7 +961,7 @@ def test_randomized_feature_combinations(case):
     seed = int(rng.integers(0, 2 ** 62))
     lens = [int(x) for x in rng.integers(0, N + 1, size=B)] if rng.integers(0, 2) else None
     mask = None
-    if rng.integers(0, 2) and (p == 0.0 or dtype == torch.float32):
+    if rng.integers(0, 2):
         shape = [(N, N), (B, N, N), (1, H, N, N), (B, H, N, N)][int(rng.integers(0, 4))]
         mask = torch.from_numpy(rng.random(shape) < 0.75)
         mask4 = mask.reshape((1,) * (4 - mask.dim()) + tuple(mask.shape)) if mask.dim() != 3 else mask[:, None]
@@ -1038,7 +1038,8 @@ def _check_masked(Q, K, V, dO, causal, scale, mask, got, dtype, p=0.0, seed=0):
         # P|V| over the visible keys only (an upper bound: the full softmax with |V| is not, the mask renormalises)
         Pm = torch.softmax((scale * Q.double() @ K.double().transpose(-1, -2)).masked_fill(~full, -math.inf), -1)
         p_absv = torch.nan_to_num(Pm, nan=0.0) @ V.double().abs()
-        bound = 2e-3 + 2.0 ** -(MANT_BITS[dtype] + 2) * p_absv + out_half_ulp(ref["O"], dtype)
+        rp = 256.0 / (256.0 - orc.dropout_threshold(p))
+        bound = rp * (2e-3 + 2.0 ** -(MANT_BITS[dtype] + (2 if p == 0.0 else 1)) * p_absv) + out_half_ulp(ref["O"], dtype)
         assert (o_err <= bound).all(), f"O err {o_err.max().item():.3e}"
         assert (L.squeeze(-1)[seen].double() - ref["L"].squeeze(-1)[seen]).abs().max() <= 2e-3
     for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
@@ -1098,12 +1099,10 @@ def test_attention_mask_equivalences_and_autograd():
         FlashAttention.apply(Q, K, V, False, 0.09, None, 0.0, None, torch.ones(N + 1, N + 1, dtype=torch.bool, device=DEV))
     with pytest.raises(ValueError):
         FlashAttention.apply(Q, K, V, False, 0.09, None, 0.0, None, torch.ones(3, N, N, dtype=torch.bool, device=DEV))
-    with pytest.raises(_lib.FlashAttentionLibraryError):   # 16-bit: mask and dropout together are not instantiated
-        FlashAttention.apply(Q, K, V, False, 0.09, None, 0.5, 1, tril)
 
 
-def test_attention_mask_with_seqlens_and_fp32_dropout():
-    """mask AND key padding (16-bit); mask AND dropout (float32 kernels take both)."""
+def test_attention_mask_with_seqlens_and_dropout():
+    """mask AND key padding; mask AND dropout (float32 and 16-bit kernels)."""
     B, H, N, D = 3, 2, 260, 64
     g = torch.Generator().manual_seed(6)
     mask = torch.rand(B, H, N, N, generator=g) < 0.6
@@ -1120,6 +1119,13 @@ def test_attention_mask_with_seqlens_and_fp32_dropout():
     mask = torch.rand(2, 1, 200, 200, generator=g) < 0.5
     got = _run_masked(Q, K, V, dO, True, 0.2, mask, None, 0.3, 777)
     _check_masked(Q, K, V, dO, True, 0.2, mask, got, torch.float32, 0.3, 777)
+    for dtype, D in ((torch.bfloat16, 128), (torch.float16, 64)):
+        Q, K, V, dO = make_inputs(96, 2, 2, 300, D, dtype)
+        mask = torch.rand(1, 2, 300, 300, generator=g) < 0.6
+        mask[0, :, 128:256, :128] = False      # an empty block and
+        mask[0, :, 128:256, 128:256] = True    # a fully visible one
+        got = _run_masked(Q, K, V, dO, False, 1.0 / math.sqrt(D), mask, None, 0.25, 4711)
+        _check_masked(Q, K, V, dO, False, 1.0 / math.sqrt(D), mask, got, dtype, 0.25, 4711)
 
 
 @pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)])

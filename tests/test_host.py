@@ -252,9 +252,6 @@ def test_c_abi_rejects_bad_dropout_arguments():
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.0, 0,
                           ctypes.byref(am), null)
     assert rc < 0 and b"FP8" in lib.fa_last_error()
-    rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 0.5, 1,
-                          ctypes.byref(am), null)
-    assert rc < 0 and b"float32 only" in lib.fa_last_error()
     rc = lib.fa_bwd_partial(null, null, null, null, null, null, null, null, null, null, 0, 1, 1, 100, 64, s, s, s, s, s, s, s,
                             1, 1.0, 0, 3, null, 0.0, 0, ctypes.byref(am), null)
     assert rc < 0 and b"cols" in lib.fa_last_error()
