@@ -44,12 +44,18 @@ class FlashAttentionLibraryError(RuntimeError):
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = REPO_ROOT / "build" / "obj"
+
+
+def _translation_units():
+    """csrc/*.cu: the C ABI (fa_api.cu) and one file per tcgen05 kernel family, compiled in parallel."""
+    return sorted(CSRC.glob("*.cu"))
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HEADER]
+    return _translation_units() + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HEADER]
 
 
 def needs_build() -> bool:
@@ -59,24 +65,43 @@ def needs_build() -> bool:
     return any(s.stat().st_mtime > t for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/fa_api.cu for sm_100a into libfa_b200.so next to this file (nvcc cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
+    """Compile csrc/*.cu for sm_100a (one nvcc process per translation unit, in parallel) and link libfa_b200.so next
+    to this file.  nvcc cross-compiles without a GPU."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise FlashAttentionLibraryError("nvcc not found; cannot build libfa_b200.so")
-    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp), str(CSRC / "fa_api.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise FlashAttentionLibraryError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
-    os.replace(tmp, LIB_PATH)
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    tag = "%d" % os.getpid()
+    flags = [*NVCC_FLAGS, *extra_flags] + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for src in _translation_units():
+        obj = OBJ_DIR / f"{src.stem}.{tag}.o"
+        jobs.append((src, obj, subprocess.Popen([nvcc, *flags, "-c", "-o", str(obj), str(src)],
+                                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    logs, failed = [], []
+    for src, obj, proc in jobs:
+        out, _ = proc.communicate()
+        logs.append(out)
+        if proc.returncode != 0:
+            failed.append(f"{src.name}:\n{out}")
+    try:
+        if failed:
+            raise FlashAttentionLibraryError("nvcc failed:\n" + "\n".join(failed))
+        if verbose:
+            print("".join(logs))
+        tmp = LIB_PATH.with_suffix(".so.tmp" + tag)
+        link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp),
+                               *[str(obj) for _, obj, _ in jobs]], capture_output=True, text=True)
+        if link.returncode != 0:
+            raise FlashAttentionLibraryError("link failed:\n" + link.stdout + link.stderr)
+        os.replace(tmp, LIB_PATH)
+    finally:
+        for _, obj, _ in jobs:
+            if obj.exists():
+                obj.unlink()
     return LIB_PATH
 
 

@@ -1,10 +1,12 @@
 // fa_api.cu — C ABI of libfa_b200.so (declared in include/fa_b200.h): argument checking, TMA tensor-map
 // encoding and kernel launches.  No torch types, no device allocation, no synchronisation.
+// The tcgen05 forward / dK,dV / dQ kernels are instantiated in fa_launch_*.cu (parallel compilation, fa_host.h).
 #include "../../include/fa_b200.h"
 
 #include "fa_bwd_fused_sm100.cuh"
 #include "fa_bwd_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
+#include "fa_host.h"
 #include "fa_merge.cuh"
 #include "fa_preprocess.cuh"
 #include "fa_simt_f32.cuh"
@@ -15,20 +17,25 @@
 #include <cstring>
 
 namespace {
-
 thread_local char g_err[512] = "";
+}
 
-int fail(int code, const char* fmt, ...) {
+int fa_host::fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
-int cuda_fail(cudaError_t e, const char* what) {
+int fa_host::cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return (int)e;
 }
+
+namespace {
+using fa_host::cuda_fail;
+using fa_host::fail;
+using fa_host::set_smem;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -56,13 +63,6 @@ int check_tensor(const char* fn, const char* name, const void* p, const int64_t 
   if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) return fail(-8, "%s: %s must be 16-byte aligned", fn, name);
   if (s[2] % gran != 0 || (H > 1 && s[1] % gran != 0) || (B > 1 && s[0] % gran != 0))
     return fail(-9, "%s: %s strides must be multiples of 16 bytes", fn, name);
-  return 0;
-}
-
-template <typename K>
-int set_smem(K kernel, int bytes) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   return 0;
 }
 
@@ -104,24 +104,7 @@ void fill3(int64_t (&dst)[3], const int64_t s[4]) {
   dst[0] = s[0], dst[1] = s[1], dst[2] = s[2];
 }
 
-// ---------------------------------------------------------------------------------------------- forward
-template <int kElt, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
-int launch_fwd16(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p, int H,
-                 int B, cudaStream_t st) {
-  using Cfg = fa::FwdCfg<kD, kElt>;
-  if constexpr (kElt < 3 && !kDrop && !kAmask) {
-    if (p.drop.thresh && p.amask) return launch_fwd16<kElt, kD, kCausal, true, true>(tq, tk, tv, p, H, B, st);
-    if (p.drop.thresh) return launch_fwd16<kElt, kD, kCausal, true, false>(tq, tk, tv, p, H, B, st);
-    if (p.amask) return launch_fwd16<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
-  }
-  auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal, kDrop, kAmask>;
-  if (int r = set_smem(kern, Cfg::kSmemBytes)) return r;
-  dim3 grid(p.q_blocks, H, B);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd launch");
-}
-
+// ---------------------------------------------------------------------------------------------- forward (float32)
 template <int kD>
 int launch_fwd32(const fa::SimtParams& p, cudaStream_t st) {
   auto kern = fa::fa_fwd_f32_kernel<kD>;
@@ -157,32 +140,6 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------- backward (16-bit)
-template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
-int launch_bwd16(const fa::BwdMaps& m, const fa::BwdParams& p, int which, cudaStream_t st) {
-  if constexpr (!kDrop && !kAmask) {
-    if (p.drop.thresh && p.amask) return launch_bwd16<kBf16, kD, kCausal, true, true>(m, p, which, st);
-    if (p.drop.thresh) return launch_bwd16<kBf16, kD, kCausal, true, false>(m, p, which, st);
-    if (p.amask) return launch_bwd16<kBf16, kD, kCausal, false, true>(m, p, which, st);
-  }
-  if (which & FA_BWD_DKDV) {
-    auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
-    if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDkdv)) return r;
-    dim3 grid((p.N + 127) / 128, p.H, p.B);
-    kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDkdv, st>>>(m.q, m.k, m.v, m.dout, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(dK/dV) launch");
-  }
-  if (which & FA_BWD_DQ) {
-    auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
-    if (int r = set_smem(kern, fa::BwdCfg<kD>::kSmemDq)) return r;
-    dim3 grid((p.N + 127) / 128, p.H, p.B);
-    kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDq, st>>>(m.q, m.k, m.v, m.dout, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(dQ) launch");
-  }
-  return 0;
-}
-
 // Workspace of the fused backward: [ticket | pad to 256 B][turn counters 2 x tiles, padded to 256 B][fp32 dQ tiles A][B]
 struct FusedLayout {
   size_t ctrl_bytes, acc_floats, total_bytes;
@@ -325,22 +282,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   if (attn_mask) p.am_sB = attn_mask_strides[0], p.am_sH = attn_mask_strides[1], p.am_sN = attn_mask_strides[2];
   if (mask && mask->blocks)
     p.ablock = mask->blocks, p.ab_sB = mask->blocks_strides[0], p.ab_sH = mask->blocks_strides[1], p.ab_sI = mask->blocks_strides[2];
-#define FA_FWD_CASE(E, DD, C) \
-  if (dtype == E && D == DD && (causal != 0) == C) return launch_fwd16<E, DD, C>(tq, tk, tv, p, H, B, st);
-  FA_FWD_CASE(FA_DTYPE_BF16, 128, true)
-  FA_FWD_CASE(FA_DTYPE_BF16, 128, false)
-  FA_FWD_CASE(FA_DTYPE_BF16, 64, true)
-  FA_FWD_CASE(FA_DTYPE_BF16, 64, false)
-  FA_FWD_CASE(FA_DTYPE_F16, 128, true)
-  FA_FWD_CASE(FA_DTYPE_F16, 128, false)
-  FA_FWD_CASE(FA_DTYPE_F16, 64, true)
-  FA_FWD_CASE(FA_DTYPE_F16, 64, false)
-  FA_FWD_CASE(FA_DTYPE_F8E4M3, 128, true)
-  FA_FWD_CASE(FA_DTYPE_F8E4M3, 128, false)
-  FA_FWD_CASE(FA_DTYPE_F8E5M2, 128, true)
-  FA_FWD_CASE(FA_DTYPE_F8E5M2, 128, false)
-#undef FA_FWD_CASE
-  return fail(-3, "fa_fwd: no kernel for dtype %d D %d", dtype, D);
+  return fa_host::launch_fwd16(dtype, D, causal != 0, tq, tk, tv, p, H, B, st);
 }
 
 int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int H, int N, int D,
@@ -494,10 +436,15 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
       for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
     }
   }
-#define FA_BWD_CASE(BF, DD, C)                                                                  \
-  if (bf == BF && D == DD && (causal != 0) == C)                                                \
-    return which == FA_BWD_FUSED ? launch_bwd16_fused<BF, DD, C>(m, p, workspace, st)           \
-                                 : launch_bwd16<BF, DD, C>(m, p, which, st);
+  if (which != FA_BWD_FUSED) {
+    if (which & FA_BWD_DKDV)
+      if (int r = fa_host::launch_bwd16_dkdv(bf != 0, D, causal != 0, m, p, st)) return r;
+    if (which & FA_BWD_DQ)
+      if (int r = fa_host::launch_bwd16_dq(bf != 0, D, causal != 0, m, p, st)) return r;
+    return 0;
+  }
+#define FA_BWD_CASE(BF, DD, C) \
+  if (bf == BF && D == DD && (causal != 0) == C) return launch_bwd16_fused<BF, DD, C>(m, p, workspace, st);
   FA_BWD_CASE(true, 128, true)
   FA_BWD_CASE(true, 128, false)
   FA_BWD_CASE(true, 64, true)

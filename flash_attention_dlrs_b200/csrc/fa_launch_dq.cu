@@ -1,0 +1,38 @@
+// fa_launch_dq.cu — instantiations and launch dispatch of the tcgen05 dQ kernel (own translation unit: see fa_host.h).
+#include "../../include/fa_b200.h"
+#include "fa_bwd_sm100.cuh"
+#include "fa_host.h"
+
+namespace {
+
+template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
+int launch(const fa::BwdMaps& m, const fa::BwdParams& p, cudaStream_t st) {
+  if constexpr (!kDrop && !kAmask) {
+    if (p.drop.thresh && p.amask) return launch<kBf16, kD, kCausal, true, true>(m, p, st);
+    if (p.drop.thresh) return launch<kBf16, kD, kCausal, true, false>(m, p, st);
+    if (p.amask) return launch<kBf16, kD, kCausal, false, true>(m, p, st);
+  }
+  auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
+  if (int r = fa_host::set_smem(kern, fa::BwdCfg<kD>::kSmemDq)) return r;
+  dim3 grid((p.N + 127) / 128, p.H, p.B);
+  kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDq, st>>>(m.q, m.k, m.v, m.dout, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fa_host::cuda_fail(e, "fa_bwd(dQ) launch");
+}
+
+}  // namespace
+
+int fa_host::launch_bwd16_dq(bool bf16, int D, bool causal, const fa::BwdMaps& m, const fa::BwdParams& p, cudaStream_t st) {
+#define FA_BWD_CASE(BF, DD, C) \
+  if (bf16 == BF && D == DD && causal == C) return launch<BF, DD, C>(m, p, st);
+  FA_BWD_CASE(true, 128, true)
+  FA_BWD_CASE(true, 128, false)
+  FA_BWD_CASE(true, 64, true)
+  FA_BWD_CASE(true, 64, false)
+  FA_BWD_CASE(false, 128, true)
+  FA_BWD_CASE(false, 128, false)
+  FA_BWD_CASE(false, 64, true)
+  FA_BWD_CASE(false, 64, false)
+#undef FA_BWD_CASE
+  return fa_host::fail(-3, "fa_bwd: no kernel for D %d", D);
+}

@@ -2,7 +2,7 @@
 # timing ablations of the elementwise stages (results are numerically wrong by construction; timing only)
 # The ablation libraries are built in the dev container first (nvcc cross-compiles; build/ travels with gpurun):
 #   for a in 0 1 2 3; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared \
-#       -DFA_ABLATE=$a -o build/libfa_ablate$a.so flash_attention_dlrs_b200/csrc/fa_api.cu; done
+#       -DFA_ABLATE=$a -o build/libfa_ablate$a.so flash_attention_dlrs_b200/csrc/*.cu; done
 mkdir -p gpurun_out build
 for a in 0 1 2 3; do
   [ -f build/libfa_ablate$a.so ] || { echo "build/libfa_ablate$a.so missing (see the header of this script)"; continue; }
