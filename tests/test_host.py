@@ -275,6 +275,8 @@ def test_attention_mask_packing_on_cpu():
     with pytest.raises(ValueError):
         am.struct(3, 4, N, torch.device("cpu"))
     assert _native.AttentionMask(torch.ones(N, N)).shape == (1, 1, N)
+    win = _native.AttentionMask.sliding_window(300, 2, 1, device="cpu")
+    assert win.rows[0, 0, 10, :300].nonzero().flatten().tolist() == [8, 9, 10, 11] and win.blocks[0, 0, 0, 2] == 0
     full = _native.AttentionMask(torch.ones(256, 256, dtype=torch.bool).tril())
     assert full.blocks.flatten().tolist() == [1, 0, 2, 1]   # diagonal blocks mixed, lower block fully visible, upper empty
     assert _native.AttentionMask(torch.ones(N, N)).blocks[0, 0].tolist() == [[2, 2, 1], [2, 2, 1], [1, 1, 1]]   # ragged edge
