@@ -158,9 +158,8 @@ class AttentionMask:
     def sliding_window(cls, N: int, left: int, right: int, device="cuda"):
         """Mask of a local-attention band: query i sees keys i - left .. i + right (combine with causal=True, or
         right = 0, for a causal window).  With block skipping the kernels' time is proportional to the band."""
-        i = torch.arange(N, device=device)
-        d = i[None, :] - i[:, None]          # key - query
-        return cls((d >= -int(left)) & (d <= int(right)))
+        band = torch.ones((N, N), dtype=torch.bool, device=device)
+        return cls(band.tril_(int(right)).triu_(-int(left)))   # in place: one byte per entry, no integer temporaries
 
     def struct(self, B: int, H: int, N: int, device):
         """ctypes fa_attn_mask for a (B, H, N, .) problem; size-1 batch / head dims broadcast (stride 0)."""

@@ -1157,3 +1157,39 @@ def test_attention_mask_block_skipping_long(dtype, D, causal):
     g2 = flash_attention_backward(q, k, v, O2, do, L2, DEV, True, causal, scale, None, 0.0, None, am)
     for a, b in zip(got, (O2, L2, *g2)):
         assert torch.equal(a, b.cpu())
+
+
+def test_attention_mask_at_the_512_block_limit_of_the_skip_lists():
+    """N = 65536 = 512 key blocks, the capacity of the kernels' shared-memory block lists: a +-200 sliding window (most of
+    the 512 x 512 blocks skipped, list indices up to 511).  Checked on windows of the sequence against the oracle on the
+    corresponding sub-problem: interior queries see exactly the same keys there, so O / L / dQ (and dK / dV further
+    inside) must agree."""
+    from flash_attention_dlrs_b200 import AttentionMask
+    B, H, N, D, W = 1, 1, 65536, 64, 200
+    scale = 0.125
+    g = torch.Generator().manual_seed(97)
+    Q, K, V, dO = ((torch.randn(B, H, N, D, generator=g)).to(torch.bfloat16) for _ in range(4))
+    am = AttentionMask.sliding_window(N, W, W, device=DEV)
+    assert am.blocks.shape[-1] == 512 and (am.blocks > 0).float().mean() < 0.01
+    q, k, v, do = (t.to(DEV) for t in (Q, K, V, dO))
+    O, L = flash_attention_forward(q, k, v, DEV, False, scale, None, 0.0, None, am)
+    dQ, dK, dV = flash_attention_backward(q, k, v, O, do, L, DEV, True, False, scale, None, 0.0, None, am)
+    torch.cuda.synchronize()
+    del am
+    for s0 in (0, 32768 - 300, N - 1100):
+        e0 = s0 + 1100
+        sub = tuple(t[:, :, s0:e0] for t in (Q, K, V, dO))
+        i = torch.arange(e0 - s0)
+        m = ((i[:, None] - i[None, :]).abs() <= W)[None, None]
+        keep = torch.ones(1, 1, e0 - s0, e0 - s0, dtype=torch.bool)
+        ref = orc.attention_dropout_grads_fp64(*(t.float() for t in sub), scale, False, keep, 0.0, m)
+        lo_q = 0 if s0 == 0 else W            # queries whose whole window lies inside the slice
+        hi_q = (e0 - s0) if e0 == N else (e0 - s0 - W)
+        lo_k = 0 if s0 == 0 else 2 * W        # keys whose queries are all such queries
+        hi_k = (e0 - s0) if e0 == N else (e0 - s0 - 2 * W)
+        got_o = O[:, :, s0:e0].cpu().double()
+        assert (got_o[:, :, lo_q:hi_q] - ref["O"][:, :, lo_q:hi_q]).abs().max() <= 2e-2
+        assert (L[:, :, s0:e0].cpu().double()[:, :, lo_q:hi_q] - ref["L"][:, :, lo_q:hi_q]).abs().max() <= 2e-3
+        assert rel_err(dQ[:, :, s0:e0].cpu()[:, :, lo_q:hi_q], ref["dQ"][:, :, lo_q:hi_q]) <= 1e-2
+        assert rel_err(dK[:, :, s0:e0].cpu()[:, :, lo_k:hi_k], ref["dK"][:, :, lo_k:hi_k]) <= 1e-2
+        assert rel_err(dV[:, :, s0:e0].cpu()[:, :, lo_k:hi_k], ref["dV"][:, :, lo_k:hi_k]) <= 1e-2
