@@ -116,7 +116,8 @@ class AttnMaskStruct(ctypes.Structure):
     """fa_attn_mask of include/fa_b200.h."""
     _fields_ = [("rows", ctypes.c_void_p), ("rows_strides", _I64x3),
                 ("cols", ctypes.c_void_p), ("cols_strides", _I64x3),
-                ("blocks", ctypes.c_void_p), ("blocks_strides", _I64x3)]
+                ("blocks", ctypes.c_void_p), ("blocks_strides", _I64x3),
+                ("window_left", ctypes.c_int32), ("window_right", ctypes.c_int32)]
 
 
 def _declare(lib):

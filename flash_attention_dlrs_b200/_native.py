@@ -128,6 +128,7 @@ class AttentionMask:
     `mask`: bool (or any dtype, non-zero = attend) of shape (N, N), (B|1, N, N) or (B|1, H|1, N, N)."""
 
     def __init__(self, mask: torch.Tensor):
+        self.window = None
         if mask.dim() == 2:
             mask = mask[None, None]
         elif mask.dim() == 3:
@@ -157,19 +158,37 @@ class AttentionMask:
     @classmethod
     def sliding_window(cls, N: int, left: int, right: int, device="cuda"):
         """Mask of a local-attention band: query i sees keys i - left .. i + right (combine with causal=True, or
-        right = 0, for a causal window).  With block skipping the kernels' time is proportional to the band."""
-        band = torch.ones((N, N), dtype=torch.bool, device=device)
-        return cls(band.tril_(int(right)).triu_(-int(left)))   # in place: one byte per entry, no integer temporaries
+        right = 0, for a causal window).  With block skipping the kernels' time is proportional to the band.
+        No mask bytes are stored: the kernels compute the band from the two numbers, and the 128 x 128 block summary
+        (which blocks to skip, which are fully visible) is computed here from them — O((N / 128)^2) memory."""
+        left, right = int(left), int(right)
+        if left < 0 or right < 0:
+            raise ValueError("sliding_window needs left, right >= 0")
+        self = cls.__new__(cls)
+        self.window = (left, right)
+        self.rows = self.cols = None
+        nb = (N + 127) // 128
+        bi = torch.arange(nb, device=device)
+        # key - query over block (i, j) ranges over [128 (j - i) - 127, 128 (j - i) + 127]
+        dmin = 128 * (bi[None, :] - bi[:, None]) - 127
+        dmax = dmin + 254
+        some = (dmax >= -left) & (dmin <= right)
+        full = (dmin >= -left) & (dmax <= right)
+        self.blocks = (some.to(torch.uint8) + full.to(torch.uint8))[None, None].contiguous()
+        self.shape = (1, 1, N)
+        self._struct = None
+        return self
 
     def struct(self, B: int, H: int, N: int, device):
         """ctypes fa_attn_mask for a (B, H, N, .) problem; size-1 batch / head dims broadcast (stride 0)."""
         Bm, Hm, Nm = self.shape
         if Nm != N or Bm not in (1, B) or Hm not in (1, H):
             raise ValueError(f"attn_mask of shape {(Bm, Hm, Nm, Nm)} does not broadcast to {(B, H, N, N)}")
-        if self.rows.device != device:
-            raise ValueError(f"attn_mask is on {self.rows.device}, the inputs on {device}")
+        if self.blocks.device != device:
+            raise ValueError(f"attn_mask is on {self.blocks.device}, the inputs on {device}")
         if self._struct is None:
             st = _lib.AttnMaskStruct()
+            st.window_left, st.window_right = self.window if self.window is not None else (-1, -1)
             for name, t in (("rows", self.rows), ("cols", self.cols), ("blocks", self.blocks)):
                 if t is None:
                     continue

@@ -94,6 +94,8 @@ int check_amask(const char* fn, const char* name, const uint8_t* m, const int64_
 
 // 128 x 128 block summary of a mask: bytes [.., query block, key block], strides {sB, sH, sI} in bytes
 int check_ablock(const char* fn, const fa_attn_mask* m) {
+  if (m && !m->rows && (m->window_left < 0 || m->window_right < 0))
+    return fail(-14, "%s: attn_mask without rows is a band mask and needs window_left, window_right >= 0", fn);
   if (!m || !m->blocks) return 0;
   const int64_t* s = m->blocks_strides;
   if (s[0] < 0 || s[1] < 0 || s[2] <= 0) return fail(-14, "%s: attn_mask->blocks strides must be non-negative (row stride positive)", fn);
@@ -195,7 +197,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 6; }
+int fa_version(void) { return 7; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -212,12 +214,12 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
                  void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
                  const fa_attn_mask* mask, void* stream) {
   g_err[0] = 0;
-  if (mask && !mask->rows) return fail(-14, "fa_fwd_peers: attn_mask->rows is null");
   const uint8_t* attn_mask = mask ? mask->rows : nullptr;
   const int64_t* attn_mask_strides = mask ? mask->rows_strides : nullptr;
   if (int r = check_amask("fa_fwd_peers", "attn_mask->rows", attn_mask, attn_mask_strides, N)) return r;
   if (int r = check_ablock("fa_fwd_peers", mask)) return r;
-  if (attn_mask && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
+  const bool band = mask && !mask->rows;
+  if (mask && (dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2))
     return fail(-14, "fa_fwd_peers: attention masks are not implemented for the FP8 forward");
   fa::DropParams drop;
   if (int r = make_drop("fa_fwd_peers", dropout_p, dropout_seed, &drop)) return r;
@@ -247,6 +249,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
     p.drop = drop;
     p.amask = attn_mask;
     if (attn_mask) p.am_s[0] = attn_mask_strides[0], p.am_s[1] = attn_mask_strides[1], p.am_s[2] = attn_mask_strides[2];
+    if (band) p.band = 1, p.win_left = mask->window_left, p.win_right = mask->window_right;
     if (mask && mask->blocks) {
       p.ablock = mask->blocks;
       for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
@@ -280,6 +283,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   p.drop = drop;
   p.amask = attn_mask;
   if (attn_mask) p.am_sB = attn_mask_strides[0], p.am_sH = attn_mask_strides[1], p.am_sN = attn_mask_strides[2];
+  if (band) p.band = 1, p.win_left = mask->window_left, p.win_right = mask->window_right;
   if (mask && mask->blocks)
     p.ablock = mask->blocks, p.ab_sB = mask->blocks_strides[0], p.ab_sH = mask->blocks_strides[1], p.ab_sI = mask->blocks_strides[2];
   return fa_host::launch_fwd16(dtype, D, causal != 0, tq, tk, tv, p, H, B, st);
@@ -345,7 +349,6 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
                    const fa_attn_mask* mask, void* stream) {
   g_err[0] = 0;
-  if (mask && !mask->rows) return fail(-14, "fa_bwd_partial: attn_mask->rows is null");
   const uint8_t* attn_mask = mask ? mask->rows : nullptr;
   const uint8_t* attn_mask_t = mask ? mask->cols : nullptr;
   const int64_t* attn_mask_strides = mask ? mask->rows_strides : nullptr;
@@ -353,7 +356,8 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   if (int r = check_amask("fa_bwd_partial", "attn_mask->rows", attn_mask, attn_mask_strides, N)) return r;
   if (int r = check_amask("fa_bwd_partial", "attn_mask->cols", attn_mask_t, attn_mask_t_strides, N)) return r;
   if (int r = check_ablock("fa_bwd_partial", mask)) return r;
-  if (attn_mask && which == FA_BWD_FUSED)
+  const bool band = mask && !mask->rows;
+  if (mask && which == FA_BWD_FUSED)
     return fail(-14, "fa_bwd_partial: FA_BWD_FUSED takes no attention mask; use the two-kernel path");
   if (attn_mask && !attn_mask_t && dtype != FA_DTYPE_F32)
     return fail(-14, "fa_bwd_partial: the 16-bit kernels need the transposed mask (attn_mask->cols) as well");
@@ -399,6 +403,7 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
     p.drop = drop;
     p.amask = attn_mask;
     if (attn_mask) p.am_s[0] = attn_mask_strides[0], p.am_s[1] = attn_mask_strides[1], p.am_s[2] = attn_mask_strides[2];
+    if (band) p.band = 1, p.win_left = mask->window_left, p.win_right = mask->window_right;
     if (mask && mask->blocks) {
       p.ablock = mask->blocks;
       for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
@@ -431,10 +436,11 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   p.amask = attn_mask, p.amask_t = attn_mask_t;
   if (attn_mask) {
     for (int i = 0; i < 3; ++i) p.am_s[i] = attn_mask_strides[i], p.amt_s[i] = attn_mask_t_strides[i];
-    if (mask->blocks) {
-      p.ablock = mask->blocks;
-      for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
-    }
+  }
+  if (band) p.band = 1, p.win_left = mask->window_left, p.win_right = mask->window_right;
+  if (mask && mask->blocks) {
+    p.ablock = mask->blocks;
+    for (int i = 0; i < 3; ++i) p.ab_s[i] = mask->blocks_strides[i];
   }
   if (which != FA_BWD_FUSED) {
     if (which & FA_BWD_DKDV)

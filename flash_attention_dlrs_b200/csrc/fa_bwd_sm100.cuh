@@ -57,6 +57,8 @@ struct BwdParams {
   // (fully visible) do not load their mask bytes
   const uint8_t* ablock;
   int64_t ab_s[3];            // {sB, sH, sI} in bytes
+  // band mask (kAmask instantiations with amask == nullptr): query i sees keys j with -win_left <= j - i <= win_right
+  int band, win_left, win_right;
 };
 
 // byte e (0..63) of a thread's 64 mask bytes held as 16 words
@@ -132,11 +134,14 @@ __device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float 
 // `drop_word` = key + word index of this thread's first element pair, `drop_shift` / kDropSecond as in fa_dropout.cuh,
 // consecutive pairs are kDropStep words apart.
 // kAmask: `mk` = this thread's 64 attention-mask bytes for the half block (non-zero = attend).
-template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP, bool kDrop = false, bool kAmask = false>
+// kBand (with kAmask): no mask bytes, the visible elements of this thread's 64 are [band_lo, band_hi].
+template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP, bool kDrop = false, bool kAmask = false,
+          bool kBand = false>
 __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
                                                      uint64_t nd_c, float sl2, int row, int col0,
                                                      uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
-                                                     float drop_rp, const uint32_t (&mk)[16]) {
+                                                     float drop_rp, const uint32_t (&mk)[16], int band_lo = 0,
+                                                     int band_hi = 0) {
   constexpr uint32_t kDropStep = kTransposed ? (1u << 15) : 1u;
   constexpr int kDropSecond = kTransposed ? 16 : 8;
 #if FA_ABLATE == 3
@@ -182,7 +187,10 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
           if (kTransposed ? (row > c0) : (c0 > row)) p0 = 0.f;
           if (kTransposed ? (row > c0 + 1) : (c0 + 1 > row)) p1 = 0.f;
         }
-        if constexpr (kAmask) {
+        if constexpr (kAmask && kBand) {
+          if (e < band_lo || e > band_hi) p0 = 0.f;
+          if (e + 1 < band_lo || e + 1 > band_hi) p1 = 0.f;
+        } else if constexpr (kAmask) {
           if (!amask_byte(mk, e)) p0 = 0.f;
           if (!amask_byte(mk, e + 1)) p1 = 0.f;
         }
@@ -212,11 +220,12 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
 // dQ kernel flavour: per-thread statistics, dS only.  The two score accumulators are copied to registers first and
 // released to the MMA warp (`sc_free`) before any arithmetic, so the next block's score MMAs overlap this stage.
 // Output: 64 values of this thread's row as 32 packed 16-bit pairs in `pd`.
-template <bool kBf16, bool kMask, bool kDrop = false, bool kAmask = false>
+template <bool kBf16, bool kMask, bool kDrop = false, bool kAmask = false, bool kBand = false>
 __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
                                                     uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32],
                                                     uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
-                                                    float drop_rp, const uint32_t (&mk)[16]) {
+                                                    float drop_rp, const uint32_t (&mk)[16], int band_lo = 0,
+                                                    int band_hi = 0) {
   uint32_t sr[64], dr[64];
   tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
   tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
@@ -251,7 +260,10 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
       if (c0 > row) p0 = 0.f;
       if (c0 + 1 > row) p1 = 0.f;
     }
-    if constexpr (kAmask) {
+    if constexpr (kAmask && kBand) {
+      if (e < band_lo || e > band_hi) p0 = 0.f;
+      if (e + 1 < band_lo || e + 1 > band_hi) p1 = 0.f;
+    } else if constexpr (kAmask) {
       if (!amask_byte(mk, e)) p0 = 0.f;
       if (!amask_byte(mk, e + 1)) p1 = 0.f;
     }
@@ -475,22 +487,37 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 
     const uint8_t* amt_row = nullptr;   // this key's row of the transposed attention mask
-    if constexpr (kAmask)
-      amt_row = p.amask_t + (int64_t)b * p.amt_s[0] + (int64_t)h * p.amt_s[1] + (int64_t)min(k0 + row, p.N - 1) * p.amt_s[2];
+    if constexpr (kAmask) {
+      if (p.amask_t)
+        amt_row = p.amask_t + (int64_t)b * p.amt_s[0] + (int64_t)h * p.amt_s[1] + (int64_t)min(k0 + row, p.N - 1) * p.amt_s[2];
+    }
 
     for (int k = 0; k < n_loop; ++k) {
       const int it = kAmask ? block_of(k) : k;
       const int s = k % NS;
       uint32_t mk[16] = {};
-      if constexpr (kAmask)
-        amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64,
-                     use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)(i_begin + it) * p.ab_s[2] + jb] == 2);
+      bool band = false;   // kAmask: this block is cut by a band mask (no mask bytes: the visible range is computed)
+      if constexpr (kAmask) {
+        const bool full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)(i_begin + it) * p.ab_s[2] + jb] == 2;
+        band = !amt_row && !full;
+        amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64, full || !amt_row);
+      }
+      // band: key j = k0 + row sees the queries i with j - win_right <= i <= j + win_left
+      const int band_base = (i_begin + it) * 128 + half * 64;
+      const int band_lo = k0 + row - p.win_right - band_base, band_hi = k0 + row + p.win_left - band_base;
       mbar_wait(&stat_full[s], (k / NS) & 1);
       mbar_wait(&sc_full[half], k & 1);
       tc_fence_after();
       const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
-      if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
+      if (kAmask && band) {
+        if (kCausal && it == 0)
+          bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask, kAmask>(
+              tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
+        else
+          bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask, kAmask>(
+              tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
+      } else if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
         bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
                                                                            drop_shift, p.drop.thresh, p.drop.rp, mk);
       else
@@ -731,8 +758,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float neg_lse = in_range ? -p.lse[stat_idx] : -INFINITY;
     if (kAmask && neg_lse == INFINITY) neg_lse = -INFINITY;   // a query that saw no key (L = -inf): P = 0
     const uint8_t* am_row = nullptr;   // this query's row of the attention mask
-    if constexpr (kAmask)
-      am_row = p.amask + (int64_t)b * p.am_s[0] + (int64_t)h * p.am_s[1] + (int64_t)min(q_row, p.N - 1) * p.am_s[2];
+    if constexpr (kAmask) {
+      if (p.amask) am_row = p.amask + (int64_t)b * p.am_s[0] + (int64_t)h * p.am_s[1] + (int64_t)min(q_row, p.N - 1) * p.am_s[2];
+    }
     const float neg_dl = in_range ? -p.delta[stat_idx] : 0.f;
     const uint64_t nl2 = f32x2_pack(neg_lse, neg_lse), nd2 = f32x2_pack(neg_dl, neg_dl);
     // dropout: this thread walks row q_row of the mask, one hash per pair of keys (fa_dropout.cuh)
@@ -771,15 +799,32 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int it = kAmask ? block_of(k) : k;   // key block of this step
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 0);   // about to wait for scores
       uint32_t mk[16] = {};
-      if constexpr (kAmask)
-        amask_load64(mk, am_row + it * 128 + half * 64,
-                     use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)ib * p.ab_s[2] + it] == 2);
+      bool band = false;   // kAmask: this block is cut by a band mask (no mask bytes: the visible range is computed)
+      if constexpr (kAmask) {
+        const bool full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)ib * p.ab_s[2] + it] == 2;
+        band = !am_row && !full;
+        amask_load64(mk, am_row + it * 128 + half * 64, full || !am_row);
+      }
+      // band: query i = q_row sees the keys j with i - win_left <= j <= i + win_right
+      const int band_base = it * 128 + half * 64;
+      const int band_lo = q_row - p.win_left - band_base, band_hi = q_row + p.win_right - band_base;
       mbar_wait(&sc_full[half], k & 1);
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 1);   // scores ready
       tc_fence_after();
       uint32_t pd[32];
       const uint32_t dw = drop_row + (uint32_t)(it * 64);
-      if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
+      if (kAmask && band) {
+        if (kCausal && it == n_it - 1)
+          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
+                                                                  dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
+        else if (tail_mask && it == n_it - 1)
+          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
+                                                                  half * 64, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mk,
+                                                                  band_lo, band_hi);
+        else
+          dq_elementwise_half<kBf16, false, kDrop, kAmask, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
+                                                                   dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
+      } else if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
         dq_elementwise_half<kBf16, true, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
                                                         drop_shift, p.drop.thresh, p.drop.rp, mk);
       else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv

@@ -71,6 +71,9 @@ struct FwdParams {
   // blocks: no skipping.
   const uint8_t* ablock;
   int64_t ab_sB, ab_sH, ab_sI;
+  // Band mask (kAmask instantiations with amask == nullptr): no mask bytes at all, query i sees the keys j with
+  // -win_left <= j - i <= win_right (sliding-window / local attention); the block summary is computed by the caller.
+  int band, win_left, win_right;
 };
 
 // kElt: element type of Q, K, V, P and O — 0 = float16, 1 = bfloat16 (tcgen05 kind::f16), 3 = FP8 E4M3, 4 = FP8 E5M2
@@ -314,8 +317,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
 
     const uint8_t* am_row = nullptr;
-    if constexpr (kAmask)
-      am_row = p.amask + (int64_t)b * p.am_sB + (int64_t)h * p.am_sH + (int64_t)min(q_row, p.N - 1) * p.am_sN;
+    if constexpr (kAmask) {
+      if (p.amask) am_row = p.amask + (int64_t)b * p.am_sB + (int64_t)h * p.am_sH + (int64_t)min(q_row, p.N - 1) * p.am_sN;
+    }
 
     float m_used = -INFINITY, l = 0.f;
     int n_seen = 0;   // kAmask: key blocks of this tile that were not skipped so far (barrier phases count these)
@@ -329,7 +333,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       const bool partial = kAmask && !(use_act && s_act[t][j] == 2);   // some entries of the block are masked out
       if constexpr (kAmask) {
-        if (partial) {
+        if (partial && am_row) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
         }
@@ -360,7 +364,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int c = 0; c < 128; ++c)
           if (c >= limit) sr[c] = 0xff800000u;         // -inf
       }
-      if (kAmask && partial) {
+      if (kAmask && partial && !am_row) {   // band mask: visible columns of this row in this block are [lo, hi]
+        const int lo = q_row - p.win_left - kv0, hi = q_row + p.win_right - kv0;
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c < lo || c > hi) sr[c] = 0xff800000u;   // -inf
+      }
+      if (kAmask && partial && am_row) {
 #pragma unroll
         for (int c = 0; c < 128; ++c) {
           const uint4& q4 = mk[c >> 4];

@@ -8,9 +8,10 @@ namespace {
 template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 int launch(const fa::BwdMaps& m, const fa::BwdParams& p, cudaStream_t st) {
   if constexpr (!kDrop && !kAmask) {
-    if (p.drop.thresh && p.amask) return launch<kBf16, kD, kCausal, true, true>(m, p, st);
+    const bool masked = p.amask != nullptr || p.band != 0;
+    if (p.drop.thresh && masked) return launch<kBf16, kD, kCausal, true, true>(m, p, st);
     if (p.drop.thresh) return launch<kBf16, kD, kCausal, true, false>(m, p, st);
-    if (p.amask) return launch<kBf16, kD, kCausal, false, true>(m, p, st);
+    if (masked) return launch<kBf16, kD, kCausal, false, true>(m, p, st);
   }
   auto kern = fa::fa_bwd_dq_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
   if (int r = fa_host::set_smem(kern, fa::BwdCfg<kD>::kSmemDq)) return r;

@@ -10,9 +10,10 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
            cudaStream_t st) {
   using Cfg = fa::FwdCfg<kD, kElt>;
   if constexpr (kElt < 3 && !kDrop && !kAmask) {
-    if (p.drop.thresh && p.amask) return launch<kElt, kD, kCausal, true, true>(tq, tk, tv, p, H, B, st);
+    const bool masked = p.amask != nullptr || p.band != 0;
+    if (p.drop.thresh && masked) return launch<kElt, kD, kCausal, true, true>(tq, tk, tv, p, H, B, st);
     if (p.drop.thresh) return launch<kElt, kD, kCausal, true, false>(tq, tk, tv, p, H, B, st);
-    if (p.amask) return launch<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
+    if (masked) return launch<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
   }
   auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal, kDrop, kAmask>;
   if (int r = fa_host::set_smem(kern, Cfg::kSmemBytes)) return r;

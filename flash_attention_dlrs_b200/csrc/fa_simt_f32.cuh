@@ -35,10 +35,22 @@ struct SimtParams {
   int64_t am_s[3];
   const uint8_t* ablock;   // optional 128 x 128 block summary [.., query block, key block]: 0 = nothing visible, skip
   int64_t ab_s[3];
+  int band, win_left, win_right;   // band mask (amask == nullptr, band != 0): -win_left <= key - query <= win_right
 };
 
-__device__ __forceinline__ bool simt_visible(const uint8_t* am_bh, int64_t am_sN, int row, int col) {
-  return am_bh == nullptr || __ldg(am_bh + (int64_t)row * am_sN + col) != 0;
+// mask of one (b, h): bytes and/or band
+struct SimtMask {
+  const uint8_t* bytes;
+  int64_t sN;
+  int band, wl, wr;
+  __device__ __forceinline__ bool any() const { return bytes != nullptr || band != 0; }
+  __device__ __forceinline__ bool visible(int row, int col) const {
+    if (band && (col - row < -wl || col - row > wr)) return false;
+    return bytes == nullptr || __ldg(bytes + (int64_t)row * sN + col) != 0;
+  }
+};
+__device__ __forceinline__ SimtMask simt_mask(const SimtParams& p, int b, int h) {
+  return SimtMask{p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr, p.am_s[2], p.band, p.win_left, p.win_right};
 }
 
 constexpr int kSimtTile = 64;
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
   }
   const uint32_t drop_thresh = p.drop.thresh;
   const uint32_t dkey = drop_thresh ? drop_key(p.drop, b * p.H + h) : 0u;
-  const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
+  const SimtMask am = simt_mask(p, b, h);
   const int n_kv = p.causal ? min((nv + 63) / 64, qb + 1) : (nv + 63) / 64;
   const uint8_t* ab_q = p.ablock ? p.ablock + b * p.ab_s[0] + h * p.ab_s[1] + (int64_t)(q0 >> 7) * p.ab_s[2] : nullptr;
   for (int jb = 0; jb < n_kv; ++jb) {
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
       for (int j = 0; j < 4; ++j) {
         const int col = k0 + tx * 4 + j;
         const bool dead = (col >= nv) || (p.causal && col > row) ||
-                          (row < nv && !simt_visible(am_bh, p.am_s[2], row, col));
+                          (row < nv && !am.visible(row, col));
         s[i][j] = dead ? -INFINITY : s[i][j] * p.scale_log2;
         mx = fmaxf(mx, s[i][j]);
       }
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(256) fa_fwd_f32_kernel(const SimtParams p) {
 __device__ __forceinline__ void simt_p_ds(float (&s)[4][4], float (&dp)[4][4], const float (&lse)[4],
                                           const float (&dl)[4], int q0, int k0, int ty, int tx, int N, int causal,
                                           float scale_log2, uint32_t dkey, uint32_t drop_thresh, float drop_rp,
-                                          const uint8_t* am_bh, int64_t am_sN) {
+                                          const SimtMask& am) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
@@ -276,7 +288,7 @@ __device__ __forceinline__ void simt_p_ds(float (&s)[4][4], float (&dp)[4][4], c
     for (int j = 0; j < 4; ++j) {
       const int col = k0 + tx * 4 + j;
       bool dead = (col >= N) || (row >= N) || (causal && col > row);
-      if (!dead && am_bh) dead = (__ldg(am_bh + (int64_t)row * am_sN + col) == 0) || lse[i] == -INFINITY;
+      if (!dead && am.any()) dead = !am.visible(row, col) || lse[i] == -INFINITY;
       const float pv = dead ? 0.f : exp2f(fmaf(s[i][j], scale_log2, -lse[i]));
       if (drop_thresh) {
         const bool keep = drop_keep(dkey, row, col, drop_thresh);
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
 
   const uint32_t dkey = p.drop.thresh ? drop_key(p.drop, b * p.H + h) : 0u;
   const float dv_mul = p.drop.thresh ? p.drop.rp : 1.0f;
-  const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
+  const SimtMask am = simt_mask(p, b, h);
   float dk[4][kAcc], dv[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -343,8 +355,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dkdv_f32_kernel(const SimtParams p
       lse[i] = row < nv ? lsep[row] : 0.f;
       dl[i] = row < nv ? dlp[row] : 0.f;
     }
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp, am_bh,
-              p.am_s[2]);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp, am);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       *reinterpret_cast<float4*>(Ps + (ty * 4 + i) * kSimtLdT + tx * 4) = make_float4(s[i][0], s[i][1], s[i][2], s[i][3]);
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
   simt_load_rowmajor<kD>(dOs, SS::kLdR, p.dout + b * p.do_s[0] + h * p.do_s[1] + (int64_t)q0 * p.do_s[2], p.do_s[2],
                          nv - q0);
   const uint32_t dkey = p.drop.thresh ? drop_key(p.drop, b * p.H + h) : 0u;
-  const uint8_t* am_bh = p.amask ? p.amask + b * p.am_s[0] + h * p.am_s[1] : nullptr;
+  const SimtMask am = simt_mask(p, b, h);
   float lse[4], dl[4], dq[4][kAcc];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -424,8 +435,7 @@ __global__ void __launch_bounds__(256) fa_bwd_dq_f32_kernel(const SimtParams p) 
     float s[4][4], dp[4][4];
     simt_scores_rt<kD>(s, Qs, SS::kLdR, Kt, ty, tx);
     simt_scores_rt<kD>(dp, dOs, SS::kLdR, Vt, ty, tx);
-    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp, am_bh,
-              p.am_s[2]);
+    simt_p_ds(s, dp, lse, dl, q0, k0, ty, tx, nv, p.causal, p.scale_log2, dkey, p.drop.thresh, p.drop.rp, am);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(dSs + (ty * 4 + i) * kSimtLdT + tx * 4) =

@@ -44,6 +44,9 @@ extern "C" {
  *   blocks [.., query block, key block] (128 x 128 blocks), optional (NULL = none): 0 = no visible entry in the block
  *          (such blocks are skipped: not loaded, no MMAs, no softmax work), 2 = every entry visible (`rows` / `cols` are
  *          not read for it), 1 = mixed.  Up to 512 blocks per row / column.
+ * Band mask (sliding-window / local attention): rows == NULL (cols ignored) and window_left, window_right >= 0 — query i
+ * sees the keys j with -window_left <= j - i <= window_right; no mask bytes are read at all, `blocks` (computed by the
+ * caller from the two numbers) gives the skipping.
  * A query with no visible key gets O = 0, lse = -inf and contributes nothing to the gradients. */
 typedef struct fa_attn_mask {
   const uint8_t* rows;
@@ -52,6 +55,7 @@ typedef struct fa_attn_mask {
   int64_t cols_strides[3];
   const uint8_t* blocks;
   int64_t blocks_strides[3];
+  int32_t window_left, window_right; /* used when rows == NULL */
 } fa_attn_mask;
 
 /* ABI version of this header (bumped on any signature change). */

@@ -1193,3 +1193,27 @@ def test_attention_mask_at_the_512_block_limit_of_the_skip_lists():
         assert rel_err(dQ[:, :, s0:e0].cpu()[:, :, lo_q:hi_q], ref["dQ"][:, :, lo_q:hi_q]) <= 1e-2
         assert rel_err(dK[:, :, s0:e0].cpu()[:, :, lo_k:hi_k], ref["dK"][:, :, lo_k:hi_k]) <= 1e-2
         assert rel_err(dV[:, :, s0:e0].cpu()[:, :, lo_k:hi_k], ref["dV"][:, :, lo_k:hi_k]) <= 1e-2
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("left,right", [(100, 30), (0, 0), (5, 400), (1000, 1000)])
+def test_band_mask_equals_the_same_mask_given_as_bytes(dtype, D, causal, left, right):
+    """AttentionMask.sliding_window (no mask bytes: the kernels compute the band, the block summary is analytic) gives
+    bit for bit what the same band gives as a byte mask, forward and backward, with dropout as well."""
+    from flash_attention_dlrs_b200 import AttentionMask
+    B, H, N = 2, 2, 700
+    scale = 1.0 / math.sqrt(D)
+    Q, K, V, dO = (t.to(DEV) for t in make_inputs(98, B, H, N, D, dtype))
+    i = torch.arange(N, device=DEV)
+    d = i[None, :] - i[:, None]
+    dense = AttentionMask((d >= -left) & (d <= right))
+    band = AttentionMask.sliding_window(N, left, right, device=DEV)
+    for p_drop, seed in ((0.0, None), (0.2, 31337)):
+        outs = []
+        for am in (dense, band):
+            O, L = flash_attention_forward(Q, K, V, DEV, causal, scale, None, p_drop, seed, am)
+            g = flash_attention_backward(Q, K, V, O, dO, L, DEV, True, causal, scale, None, p_drop, seed, am)
+            outs.append((O, L, *g))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 6
+    assert lib.fa_version() == 7
     assert isinstance(lib.fa_last_error(), bytes)
 
 
@@ -275,8 +275,21 @@ def test_attention_mask_packing_on_cpu():
     with pytest.raises(ValueError):
         am.struct(3, 4, N, torch.device("cpu"))
     assert _native.AttentionMask(torch.ones(N, N)).shape == (1, 1, N)
-    win = _native.AttentionMask.sliding_window(300, 2, 1, device="cpu")
-    assert win.rows[0, 0, 10, :300].nonzero().flatten().tolist() == [8, 9, 10, 11] and win.blocks[0, 0, 0, 2] == 0
+    win = _native.AttentionMask.sliding_window(300, 2, 1, device="cpu")       # band mask: no bytes, analytic block summary
+    assert win.rows is None and win.window == (2, 1)
+    i = torch.arange(300)
+    dense = _native.AttentionMask(((i[None, :] - i[:, None]) >= -2) & ((i[None, :] - i[:, None]) <= 1))
+    assert torch.equal(win.blocks > 0, dense.blocks > 0) and win.blocks[0, 0, 0, 2] == 0
+    for left, right in ((0, 0), (127, 0), (128, 5), (300, 300), (1000, 0)):
+        w = _native.AttentionMask.sliding_window(700, left, right, device="cpu")
+        d = _native.AttentionMask(((i700 := torch.arange(700))[None, :] - i700[:, None] >= -left)
+                                  & (i700[None, :] - i700[:, None] <= right))
+        assert torch.equal(w.blocks > 0, d.blocks > 0), (left, right)
+        assert ((w.blocks == 2) <= (d.blocks[..., :w.blocks.shape[-2], :] >= 1)).all()   # "full" only where something is visible
+        inner = d.blocks[0, 0, :5, :5]   # blocks not touching the ragged edge: the two summaries agree exactly
+        assert torch.equal(w.blocks[0, 0, :5, :5], inner), (left, right)
+    st = win.struct(2, 4, 300, torch.device("cpu"))
+    assert not st.rows and st.window_left == 2 and st.window_right == 1
     full = _native.AttentionMask(torch.ones(256, 256, dtype=torch.bool).tril())
     assert full.blocks.flatten().tolist() == [1, 0, 2, 1]   # diagonal blocks mixed, lower block fully visible, upper empty
     assert _native.AttentionMask(torch.ones(N, N)).blocks[0, 0].tolist() == [[2, 2, 1], [2, 2, 1], [1, 1, 1]]   # ragged edge

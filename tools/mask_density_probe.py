@@ -29,7 +29,7 @@ def t(fn, reps=10):
 
 i = torch.arange(N, device=dev)
 for w in (0, 128, 512, 1024, 2048, 4096, 8192):
-    am = AttentionMask((i[:, None] - i[None, :]).abs() <= w)
+    am = AttentionMask.sliding_window(N, w, w, device=dev) if os.environ.get("BAND") else AttentionMask((i[:, None] - i[None, :]).abs() <= w)
     kw = dict(attn_mask=am)
     O, L = _native.forward(Q, K, V, False, sc, **kw)
     delta = _native.backward_preprocess(O, dO)
