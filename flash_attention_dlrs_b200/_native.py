@@ -120,10 +120,11 @@ def _dropout_args(dropout_p, dropout_seed):
 
 
 class AttentionMask:
-    """An arbitrary attention mask in the layout the kernels read (include/fa_b200.h, `attn_mask`): one byte per
-    (query, key), non-zero = attend, row pitch rounded up to 128 bytes — once as [.., query, key] (forward, dQ kernel)
-    and once transposed [.., key, query] (dK/dV kernel).  Build it once and pass it as `attn_mask` to reuse the packed
-    copies across calls; a plain bool tensor is wrapped on the fly.
+    """An arbitrary attention mask in the layout the kernels read (include/fa_b200.h, `fa_attn_mask`): one BIT per
+    (query, key), 1 = attend, 16 bytes per row and 128-key block — once as [.., query, key / 8] (forward, dQ kernel)
+    and once transposed [.., key, query / 8] (dK/dV kernel) — plus a byte per 128 x 128 block saying whether the block
+    is empty, mixed or fully visible.  Build it once and pass it as `attn_mask` to reuse the packed copies across calls;
+    a plain bool tensor is wrapped on the fly.
 
     `mask`: bool (or any dtype, non-zero = attend) of shape (N, N), (B|1, N, N) or (B|1, H|1, N, N)."""
 
@@ -139,10 +140,12 @@ class AttentionMask:
         Bm, Hm, N, _ = m.shape
         pitch = (N + 127) // 128 * 128
 
-        def pack(x):
-            buf = torch.zeros((Bm, Hm, N, pitch), dtype=torch.uint8, device=x.device)
+        weights = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.int16, device=m.device)
+
+        def pack(x):   # (.., N, N) bool -> (.., N, pitch / 8) uint8, entry j = bit (j & 7) of byte (j >> 3)
+            buf = torch.zeros((Bm, Hm, N, pitch), dtype=torch.int16, device=x.device)
             buf[..., :N] = x
-            return buf
+            return (buf.view(Bm, Hm, N, pitch // 8, 8) * weights).sum(-1).to(torch.uint8).contiguous()
 
         self.rows, self.cols = pack(m), pack(m.transpose(-1, -2))
         # 128 x 128 block summary: 0 = nothing of block (i, j) is visible (the kernels skip it), 2 = everything is

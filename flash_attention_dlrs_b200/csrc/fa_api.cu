@@ -78,15 +78,15 @@ int make_drop(const char* fn, float dropout_p, uint64_t seed, fa::DropParams* d)
   return 0;
 }
 
-// attention mask: bytes [.., row, col], non-zero = attend; strides {sB, sH, sRow} in bytes (sB / sH may be 0 = broadcast)
+// attention mask: one bit per entry [.., row, col / 8], 1 = attend; strides {sB, sH, sRow} in bytes (sB / sH may be 0 = broadcast)
 int check_amask(const char* fn, const char* name, const uint8_t* m, const int64_t s[3], int N) {
   if (!m) return 0;
   if (!s) return fail(-14, "%s: %s given without strides", fn, name);
-  const int64_t pitch = ((int64_t)N + 127) / 128 * 128;
+  const int64_t pitch = ((int64_t)N + 127) / 128 * 16;   // 16 bytes of bits per 128-entry block
   if ((reinterpret_cast<uintptr_t>(m) & 15u) != 0) return fail(-14, "%s: %s must be 16-byte aligned", fn, name);
   if (s[2] < pitch || s[2] % 16 != 0)
-    return fail(-14, "%s: %s row pitch must be a multiple of 16 bytes and >= N rounded up to 128 (%lld), got %lld", fn, name,
-                (long long)pitch, (long long)s[2]);
+    return fail(-14, "%s: %s row pitch must be a multiple of 16 bytes and >= 16 bytes per 128 entries (%lld), got %lld", fn,
+                name, (long long)pitch, (long long)s[2]);
   if (s[0] < 0 || s[1] < 0 || s[0] % 16 != 0 || s[1] % 16 != 0)
     return fail(-14, "%s: %s batch / head strides must be non-negative multiples of 16 bytes (0 = broadcast)", fn, name);
   return 0;
@@ -197,7 +197,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 7; }
+int fa_version(void) { return 8; }
 
 const char* fa_last_error(void) { return g_err; }
 

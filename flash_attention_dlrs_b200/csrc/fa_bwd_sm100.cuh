@@ -47,9 +47,9 @@ struct BwdParams {
   float scale, scale_log2;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; see FwdParams::seqlens
   DropParams drop;     // dropout of the attention probabilities (kDrop instantiations only), fa_dropout.cuh
-  // Arbitrary attention mask (kAmask instantiations only), bytes, non-zero = attend; see FwdParams::amask.  The dQ kernel
-  // walks query rows of `amask` [.., query, key]; the dK/dV kernel walks key rows of `amask_t` [.., key, query], the same
-  // mask transposed (made once by the caller), so both read 64 contiguous bytes per thread and half block.
+  // Arbitrary attention mask (kAmask instantiations only), one bit per entry, 1 = attend; see FwdParams::amask.  The dQ
+  // kernel walks query rows of `amask` [.., query, key]; the dK/dV kernel walks key rows of `amask_t` [.., key, query],
+  // the same mask transposed (made once by the caller), so both read 8 contiguous bytes per thread and half block.
   const uint8_t *amask, *amask_t;
   int64_t am_s[3], amt_s[3];  // {sB, sH, sRow} in bytes
   // optional block summary [.., query block, key block] (see FwdParams::ablock): both kernels loop over the blocks
@@ -61,21 +61,17 @@ struct BwdParams {
   int band, win_left, win_right;
 };
 
-// byte e (0..63) of a thread's 64 mask bytes held as 16 words
-__device__ __forceinline__ bool amask_byte(const uint32_t (&mk)[16], int e) {
-  return (mk[e >> 2] & (0xffu << (8 * (e & 3)))) != 0u;
+// bit e (0..63) of a thread's 64 mask bits held as 2 words
+__device__ __forceinline__ bool amask_byte(const uint32_t (&mk)[2], int e) {
+  return (mk[e >> 5] & (1u << (e & 31))) != 0u;
 }
-__device__ __forceinline__ void amask_load64(uint32_t (&mk)[16], const uint8_t* src, bool full = false) {
+__device__ __forceinline__ void amask_load64(uint32_t (&mk)[2], const uint8_t* src, bool full = false) {
   if (full) {   // block summary says every entry is visible
-#pragma unroll
-    for (int i = 0; i < 16; ++i) mk[i] = 0x01010101u;
+    mk[0] = mk[1] = 0xffffffffu;
     return;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
-    mk[4 * i] = v.x, mk[4 * i + 1] = v.y, mk[4 * i + 2] = v.z, mk[4 * i + 3] = v.w;
-  }
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+  mk[0] = v.x, mk[1] = v.y;
 }
 
 template <int kD>
@@ -140,7 +136,7 @@ template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP
 __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
                                                      uint64_t nd_c, float sl2, int row, int col0,
                                                      uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
-                                                     float drop_rp, const uint32_t (&mk)[16], int band_lo = 0,
+                                                     float drop_rp, const uint32_t (&mk)[2], int band_lo = 0,
                                                      int band_hi = 0) {
   constexpr uint32_t kDropStep = kTransposed ? (1u << 15) : 1u;
   constexpr int kDropSecond = kTransposed ? 16 : 8;
@@ -224,7 +220,7 @@ template <bool kBf16, bool kMask, bool kDrop = false, bool kAmask = false, bool 
 __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
                                                     uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32],
                                                     uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
-                                                    float drop_rp, const uint32_t (&mk)[16], int band_lo = 0,
+                                                    float drop_rp, const uint32_t (&mk)[2], int band_lo = 0,
                                                     int band_hi = 0) {
   uint32_t sr[64], dr[64];
   tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
@@ -495,12 +491,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int k = 0; k < n_loop; ++k) {
       const int it = kAmask ? block_of(k) : k;
       const int s = k % NS;
-      uint32_t mk[16] = {};
+      uint32_t mk[2] = {};
       bool band = false;   // kAmask: this block is cut by a band mask (no mask bytes: the visible range is computed)
       if constexpr (kAmask) {
         const bool full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)(i_begin + it) * p.ab_s[2] + jb] == 2;
         band = !amt_row && !full;
-        amask_load64(mk, amt_row + (i_begin + it) * 128 + half * 64, full || !amt_row);
+        amask_load64(mk, amt_row + (i_begin + it) * 16 + half * 8, full || !amt_row);
       }
       // band: key j = k0 + row sees the queries i with j - win_right <= i <= j + win_left
       const int band_base = (i_begin + it) * 128 + half * 64;
@@ -798,12 +794,12 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int k = 0; k < n_loop; ++k) {
       const int it = kAmask ? block_of(k) : k;   // key block of this step
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 0);   // about to wait for scores
-      uint32_t mk[16] = {};
+      uint32_t mk[2] = {};
       bool band = false;   // kAmask: this block is cut by a band mask (no mask bytes: the visible range is computed)
       if constexpr (kAmask) {
         const bool full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)ib * p.ab_s[2] + it] == 2;
         band = !am_row && !full;
-        amask_load64(mk, am_row + it * 128 + half * 64, full || !am_row);
+        amask_load64(mk, am_row + it * 16 + half * 8, full || !am_row);
       }
       // band: query i = q_row sees the keys j with i - win_left <= j <= i + win_right
       const int band_base = it * 128 + half * 64;

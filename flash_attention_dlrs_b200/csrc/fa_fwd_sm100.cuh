@@ -58,10 +58,10 @@ struct FwdParams {
   const int* seqlens;
   // Dropout of the attention probabilities (kDrop instantiations only; 16-bit dtypes): see fa_dropout.cuh.
   DropParams drop;
-  // Arbitrary attention mask (kAmask instantiations only; 16-bit dtypes): one byte per (query, key), non-zero = attend,
-  // combined (AND) with the causal flag and seqlens.  Row pitch am_sN is a multiple of 128 bytes >= N rounded up to 128
-  // (so 16-byte loads of a key block stay inside the row); am_sB / am_sH may be 0 (broadcast).  A row with no visible
-  // key gives O = 0, L = -inf.
+  // Arbitrary attention mask (kAmask instantiations only; 16-bit dtypes): one BIT per (query, key), 1 = attend (key j of
+  // a row is bit j & 7 of byte j >> 3), combined (AND) with the causal flag and seqlens.  Row pitch am_sN is a multiple
+  // of 16 bytes >= N rounded up to 128, / 8 (a key block is one 16-byte load per row: four registers, held while the
+  // thread waits for S); am_sB / am_sH may be 0 (broadcast).  A row with no visible key gives O = 0, L = -inf.
   const uint8_t* amask;
   int64_t am_sB, am_sH, am_sN;
   // Optional block summary of the mask: ablock[.., i, j] != 0 iff some (query, key) of the 128 x 128 block (i, j) is
@@ -327,16 +327,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int u = 0; u < n_mine; ++u) {
       const int j = kAmask ? block_of(u) : u;
       if (kAmask && j >= my_nkv) break;
-      uint4 mk[kAmask ? 8 : 1];   // this row's 128 mask bytes of key block j, requested before the wait for S
+      uint4 mk = make_uint4(0u, 0u, 0u, 0u);   // this row's 128 mask bits of key block j, requested before the wait for S
       if constexpr (kAmask) {
         if (!active(t, j)) continue;   // skipped block: nobody touches this tile's barriers for it
       }
       const bool partial = kAmask && !(use_act && s_act[t][j] == 2);   // some entries of the block are masked out
       if constexpr (kAmask) {
-        if (partial && am_row) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(am_row + j * 128) + i);
-        }
+        if (partial && am_row) mk = __ldg(reinterpret_cast<const uint4*>(am_row + j * 16));
       }
       const int c = kAmask ? n_seen : j;
       mbar_wait(&s_full[t], c & 1);
@@ -357,25 +354,26 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int kv0 = j * 128;
       const bool diag = kCausal && (kv0 + 127 > q0 + 128 * t);   // block touches the diagonal
       const bool ragged = (kv0 + 128 > nv);
-      if (diag || ragged) {
+      const bool band_cut = kAmask && partial && !am_row;   // band mask (no bytes): the band's edge crosses this block
+      if (diag || ragged || band_cut) {
         int limit = nv - kv0;                          // first invalid column (ragged / padded keys)
         if (kCausal) limit = min(limit, q_row - kv0 + 1);
+        int lo = 0;                                    // first visible column (band masks only)
+        if constexpr (kAmask) {
+          if (band_cut) {
+            limit = min(limit, q_row + p.win_right - kv0 + 1);
+            lo = q_row - p.win_left - kv0;
+          }
+        }
 #pragma unroll
         for (int c = 0; c < 128; ++c)
-          if (c >= limit) sr[c] = 0xff800000u;         // -inf
-      }
-      if (kAmask && partial && !am_row) {   // band mask: visible columns of this row in this block are [lo, hi]
-        const int lo = q_row - p.win_left - kv0, hi = q_row + p.win_right - kv0;
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c < lo || c > hi) sr[c] = 0xff800000u;   // -inf
+          if (c >= limit || (kAmask && c < lo)) sr[c] = 0xff800000u;   // -inf
       }
       if (kAmask && partial && am_row) {
 #pragma unroll
         for (int c = 0; c < 128; ++c) {
-          const uint4& q4 = mk[c >> 4];
-          const uint32_t w = ((c >> 2) & 3) == 0 ? q4.x : ((c >> 2) & 3) == 1 ? q4.y : ((c >> 2) & 3) == 2 ? q4.z : q4.w;
-          if (!(w & (0xffu << (8 * (c & 3))))) sr[c] = 0xff800000u;   // -inf
+          const uint32_t w = (c >> 5) == 0 ? mk.x : (c >> 5) == 1 ? mk.y : (c >> 5) == 2 ? mk.z : mk.w;
+          if (!(w & (1u << (c & 31)))) sr[c] = 0xff800000u;   // -inf
         }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;

@@ -30,7 +30,7 @@ struct SimtParams {
   int causal;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; rows past it are loaded as zeros
   DropParams drop;     // dropout of the attention probabilities (thresh = 0: off), fa_dropout.cuh
-  // arbitrary attention mask, bytes [.., query, key], non-zero = attend (nullptr: none); strides in bytes, sB / sH may be 0
+  // arbitrary attention mask, one bit per entry [.., query, key / 8], 1 = attend (nullptr: none); strides in bytes, sB / sH may be 0
   const uint8_t* amask;
   int64_t am_s[3];
   const uint8_t* ablock;   // optional 128 x 128 block summary [.., query block, key block]: 0 = nothing visible, skip
@@ -46,7 +46,7 @@ struct SimtMask {
   __device__ __forceinline__ bool any() const { return bytes != nullptr || band != 0; }
   __device__ __forceinline__ bool visible(int row, int col) const {
     if (band && (col - row < -wl || col - row > wr)) return false;
-    return bytes == nullptr || __ldg(bytes + (int64_t)row * sN + col) != 0;
+    return bytes == nullptr || ((__ldg(bytes + (int64_t)row * sN + (col >> 3)) >> (col & 7)) & 1) != 0;
   }
 };
 __device__ __forceinline__ SimtMask simt_mask(const SimtParams& p, int b, int h) {

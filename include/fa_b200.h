@@ -35,13 +35,14 @@ extern "C" {
 #define FA_DTYPE_F8E5M2 4 /* forward only, D = 128; the FP8 type of the reference's dtype map, flash_attention_torch.py:15-16 */
 
 /* An arbitrary attention mask (the general form of the "masking" on the reference's roadmap, README.md:35-37), ANDed with
- * `causal` and `seqlens`.  All pointers are device pointers to BYTES, non-zero = attend; strides are {sB, sH, sRow} in
- * bytes, sB / sH may be 0 (one mask for all batch elements / heads).
- *   rows   [.., query, key]: read by the forward and the dQ kernel.  Row pitch a multiple of 16 and at least N rounded up
- *          to 128 (kernels read whole 16-byte groups of a 128-key block), base 16-byte aligned.
+ * `causal` and `seqlens`.  All pointers are device pointers; strides are {sB, sH, sRow} in bytes, sB / sH may be 0 (one
+ * mask for all batch elements / heads).
+ *   rows   [.., query, key / 8]: one BIT per entry, 1 = attend; key j of a row is bit (j & 7) of byte (j >> 3).  Read by
+ *          the forward and the dQ kernel.  Row pitch a multiple of 16 bytes and at least 16 bytes per 128 keys (a key
+ *          block is one 16-byte load per row), base 16-byte aligned.
  *   cols   [.., key, query]: the same mask transposed, same layout rules; read by the dK/dV kernel (16-bit dtypes;
  *          float32 reads `rows` only and accepts NULL).  Not used by the forward.
- *   blocks [.., query block, key block] (128 x 128 blocks), optional (NULL = none): 0 = no visible entry in the block
+ *   blocks [.., query block, key block] (128 x 128 blocks), one BYTE per block, optional (NULL = none): 0 = no visible entry in the block
  *          (such blocks are skipped: not loaded, no MMAs, no softmax work), 2 = every entry visible (`rows` / `cols` are
  *          not read for it), 1 = mixed.  Up to 512 blocks per row / column.
  * Band mask (sliding-window / local attention): rows == NULL (cols ignored) and window_left, window_right >= 0 — query i

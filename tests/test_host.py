@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.fa_version() == 7
+    assert lib.fa_version() == 8
     assert isinstance(lib.fa_last_error(), bytes)
 
 
@@ -244,11 +244,11 @@ def test_c_abi_rejects_bad_dropout_arguments():
     # attention mask (fa_attn_mask): row pitch must cover N rounded up to 128 and keep 16-byte groups aligned
     am = _lib.AttnMaskStruct()
     am.rows = 4096
-    am.rows_strides = (ctypes.c_int64 * 3)(0, 0, 100)
+    am.rows_strides = (ctypes.c_int64 * 3)(0, 0, 8)
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 64, s, s, s, s, 1, 1.0, 0, 0, peers, null, 0.0, 0,
                           ctypes.byref(am), null)
     assert rc < 0 and b"row pitch" in lib.fa_last_error()
-    am.rows_strides = (ctypes.c_int64 * 3)(0, 0, 128)
+    am.rows_strides = (ctypes.c_int64 * 3)(0, 0, 16)
     rc = lib.fa_fwd_peers(null, null, null, null, null, 1, 1, 100, 128, s, s, s, s, 3, 1.0, 0, 0, peers, null, 0.0, 0,
                           ctypes.byref(am), null)
     assert rc < 0 and b"FP8" in lib.fa_last_error()
@@ -264,14 +264,15 @@ def test_attention_mask_packing_on_cpu():
     m[0, 0, 5, 290] = True        # block (0, 2)
     m[1, 0, 200, 130] = True      # block (1, 1)
     am = _native.AttentionMask(m)
-    assert am.rows.shape == (2, 1, N, 384) and am.rows.stride(-2) == 384
-    assert am.rows[0, 0, 5, 290] == 1 and am.cols[0, 0, 290, 5] == 1 and am.rows.sum() == 2 and am.cols.sum() == 2
+    assert am.rows.shape == (2, 1, N, 48) and am.rows.stride(-2) == 48            # one bit per entry, 16 bytes per 128 keys
+    assert am.rows[0, 0, 5, 290 >> 3] == 1 << (290 & 7) and am.cols[0, 0, 290, 5 >> 3] == 1 << 5
+    assert am.rows[1, 0, 200, 130 >> 3] == 1 << (130 & 7) and (am.rows != 0).sum() == 2 and (am.cols != 0).sum() == 2
     want = torch.zeros(2, 1, 3, 3, dtype=torch.uint8)
     want[0, 0, 0, 2] = 1
     want[1, 0, 1, 1] = 1
     assert torch.equal(am.blocks, want)
     st = am.struct(2, 4, N, torch.device("cpu"))
-    assert st.rows_strides[1] == 0 and st.rows_strides[2] == 384 and st.blocks_strides[2] == 3
+    assert st.rows_strides[1] == 0 and st.rows_strides[2] == 48 and st.blocks_strides[2] == 3
     with pytest.raises(ValueError):
         am.struct(3, 4, N, torch.device("cpu"))
     assert _native.AttentionMask(torch.ones(N, N)).shape == (1, 1, N)
