@@ -41,11 +41,14 @@ class FlashAttentionLibraryError(RuntimeError):
     """libfa_b200.so is missing, failed to load, or one of its entry points returned an error."""
 
 
+# -lineinfo only adds line tables for `ncu --import-source`: the SASS is the same with and without it
+# (profiles/r02_build_flags.txt compares the two instruction streams).  FA_B200_DEBUG=1 builds the debug flavour:
+# mbarrier watchdog on (sm100_ptx.cuh).
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
-]
+] + (["-DFA_WATCHDOG=1"] if os.environ.get("FA_B200_DEBUG") == "1" else [])
 OBJ_DIR = REPO_ROOT / "build" / "obj"
 
 

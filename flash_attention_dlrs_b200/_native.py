@@ -306,7 +306,8 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
         delta = backward_preprocess(o, do)
     sl, sl_ptr = _seqlens_arg(seqlens, B, Q.device)
     new = torch.empty if sl is None else torch.zeros   # padded rows are not written by the kernels
-    dQ, dK, dV = new((3, B, H, N, d_run), dtype=Q.dtype, device=Q.device).unbind(0)   # one allocation
+    # three independent allocations: a caller that keeps only one gradient alive must not pin the other two
+    dQ, dK, dV = (new((B, H, N, d_run), dtype=Q.dtype, device=Q.device) for _ in range(3))
     if which is None:
         which = BWD_DKDV | BWD_DQ
     ws_bytes = lib.fa_bwd_workspace_bytes(B, H, N, d_run, code, int(bool(causal)), int(which))

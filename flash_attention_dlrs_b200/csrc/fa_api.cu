@@ -35,7 +35,6 @@ int fa_host::cuda_fail(cudaError_t e, const char* what) {
 namespace {
 using fa_host::cuda_fail;
 using fa_host::fail;
-using fa_host::set_smem;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -111,7 +110,8 @@ template <int kD>
 int launch_fwd32(const fa::SimtParams& p, cudaStream_t st) {
   auto kern = fa::fa_fwd_f32_kernel<kD>;
   const int bytes = fa::SimtSmem<kD>::fwd_floats * 4;
-  if (int r = set_smem(kern, bytes)) return r;
+  static std::atomic<uint64_t> smem_set{0};
+  if (int r = fa_host::set_smem_once(kern, bytes, smem_set)) return r;
   dim3 grid((p.N + 63) / 64, p.H, p.B);
   kern<<<grid, 256, bytes, st>>>(p);
   cudaError_t e = cudaGetLastError();
@@ -123,7 +123,8 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
   if (which & FA_BWD_DKDV) {
     auto kern = fa::fa_bwd_dkdv_f32_kernel<kD>;
     const int bytes = fa::SimtSmem<kD>::dkdv_floats * 4;
-    if (int r = set_smem(kern, bytes)) return r;
+    static std::atomic<uint64_t> smem_set{0};
+    if (int r = fa_host::set_smem_once(kern, bytes, smem_set)) return r;
     dim3 grid((p.N + 63) / 64, p.H, p.B);
     kern<<<grid, 256, bytes, st>>>(p);
     cudaError_t e = cudaGetLastError();
@@ -132,7 +133,8 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
   if (which & FA_BWD_DQ) {
     auto kern = fa::fa_bwd_dq_f32_kernel<kD>;
     const int bytes = fa::SimtSmem<kD>::dq_floats * 4;
-    if (int r = set_smem(kern, bytes)) return r;
+    static std::atomic<uint64_t> smem_set{0};
+    if (int r = fa_host::set_smem_once(kern, bytes, smem_set)) return r;
     dim3 grid((p.N + 63) / 64, p.H, p.B);
     kern<<<grid, 256, bytes, st>>>(p);
     cudaError_t e = cudaGetLastError();
@@ -172,7 +174,8 @@ int launch_bwd16_fused(const fa::BwdMaps& m, const fa::BwdParams& p, void* works
   cudaError_t e = cudaMemsetAsync(ws, 0, L.ctrl_bytes, st);
   if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(fused) cudaMemsetAsync");
   auto kern = fa::fa_bwd_fused_kernel<kBf16, kD, kCausal>;
-  if (int r = set_smem(kern, fa::FusedCfg<kD>::kSmemBytes)) return r;
+  static std::atomic<uint64_t> smem_set{0};
+  if (int r = fa_host::set_smem_once(kern, fa::FusedCfg<kD>::kSmemBytes, smem_set)) return r;
   kern<<<(unsigned)L.tiles, fa::FusedCfg<kD>::kThreads, fa::FusedCfg<kD>::kSmemBytes, st>>>(m.q, m.k, m.v, m.dout, fp);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(fused) launch");
@@ -266,8 +269,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   const bool f8 = dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2;
   CUtensorMap tq, tk, tv;
   auto encode = [&](CUtensorMap* m, const void* ptr, const int64_t* st4) {
-    return f8 ? fa::make_tmap_bhnd_8bit(m, ptr, B, H, N, D, st4[0], st4[1], st4[2], 128)
-              : fa::make_tmap_bhnd_16bit(m, ptr, bf, B, H, N, D, st4[0], st4[1], st4[2], 128);
+    return fa::cached_tmap_bhnd(m, ptr, f8 ? 2 : bf, B, H, N, D, st4[0], st4[1], st4[2], 128);
   };
   if (int r = encode(&tq, q, q_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
   if (int r = encode(&tk, k, k_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
@@ -418,13 +420,13 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
 
   const int bf = dtype == FA_DTYPE_BF16;
   fa::BwdMaps m;
-  if (int r = fa::make_tmap_bhnd_16bit(&m.q, q, bf, B, H, N, D, q_strides[0], q_strides[1], q_strides[2], 128))
+  if (int r = fa::cached_tmap_bhnd(&m.q, q, bf, B, H, N, D, q_strides[0], q_strides[1], q_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
-  if (int r = fa::make_tmap_bhnd_16bit(&m.k, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 128))
+  if (int r = fa::cached_tmap_bhnd(&m.k, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
-  if (int r = fa::make_tmap_bhnd_16bit(&m.v, v, bf, B, H, N, D, v_strides[0], v_strides[1], v_strides[2], 128))
+  if (int r = fa::cached_tmap_bhnd(&m.v, v, bf, B, H, N, D, v_strides[0], v_strides[1], v_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
-  if (int r = fa::make_tmap_bhnd_16bit(&m.dout, dout, bf, B, H, N, D, do_strides[0], do_strides[1], do_strides[2], 128))
+  if (int r = fa::cached_tmap_bhnd(&m.dout, dout, bf, B, H, N, D, do_strides[0], do_strides[1], do_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(dout) failed (%d)", r);
   fa::BwdParams p{};
   p.lse = lse, p.delta = delta, p.dq = dq, p.dk = dk, p.dv = dv;

@@ -4,6 +4,8 @@
 // that nvcc compiles them in parallel (_lib.build); fa_api.cu calls the per-kernel dispatchers declared here.
 #pragma once
 
+#include <atomic>
+#include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -23,6 +25,19 @@ template <typename K>
 int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  return 0;
+}
+// The same, once per kernel instantiation and device instead of on every launch: `done` is a bit mask of the devices
+// the attribute has been set on, owned by the caller (one static per instantiation — the function-pointer TYPE is shared
+// by all instantiations, so it cannot live here).  Thread safe: a lost race only repeats an idempotent call.
+template <typename K>
+int set_smem_once(K kernel, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_smem(kernel, bytes);
+  const uint64_t bit = 1ull << dev;
+  if (done.load(std::memory_order_acquire) & bit) return 0;
+  if (int r = set_smem(kernel, bytes)) return r;
+  done.fetch_or(bit, std::memory_order_release);
   return 0;
 }
 

@@ -16,7 +16,8 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     if (masked) return launch<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
   }
   auto kern = fa::fa_fwd_kernel<kElt, kD, kCausal, kDrop, kAmask>;
-  if (int r = fa_host::set_smem(kern, Cfg::kSmemBytes)) return r;
+  static std::atomic<uint64_t> smem_set{0};   // per instantiation: devices whose attribute is set
+  if (int r = fa_host::set_smem_once(kern, Cfg::kSmemBytes, smem_set)) return r;
   dim3 grid(p.q_blocks, H, B);
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();

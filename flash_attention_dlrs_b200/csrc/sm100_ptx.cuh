@@ -19,11 +19,13 @@
 namespace fa {
 
 // ----------------------------------------------------------------------------------------------
-// Debug watchdog: every mbarrier wait gives up after ~2 s of GPU time and traps, so a
-// protocol bug surfaces as a launch failure instead of a hung box.
+// Debug watchdog (debug builds only: -DFA_WATCHDOG=1, `FA_B200_DEBUG=1 python -c "import __graft_entry__ as g; g.build()"`):
+// every mbarrier wait gives up after ~2 s of GPU time and traps, so a protocol bug surfaces as a launch
+// failure instead of a hung box.  Off in the production library: the slow path of every wait is then a bare
+// try_wait loop (no clock64, no printf, fewer live registers in the hot loops).
 // ----------------------------------------------------------------------------------------------
 #ifndef FA_WATCHDOG
-#define FA_WATCHDOG 1
+#define FA_WATCHDOG 0
 #endif
 #ifndef FA_WATCHDOG_CYCLES
 #define FA_WATCHDOG_CYCLES 4000000000LL

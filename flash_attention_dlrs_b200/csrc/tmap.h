@@ -66,4 +66,42 @@ inline int make_tmap_bhnd_8bit(CUtensorMap* out, const void* base, int B, int H,
   return r == CUDA_SUCCESS ? 0 : -(200 + (int)r);
 }
 
+// Encoded tensor maps are pure functions of (address, element type, shape, strides, box): keep the last few per thread so
+// that a training loop launching on the same buffers does not pay cuTensorMapEncodeTiled (~1 us each, 3-4 per launch)
+// on every call.  Thread-local: no locks on the launch path; an entry holds no reference to the memory it describes.
+struct TmapKey {
+  const void* base;
+  int kind;   // 0 f16, 1 bf16, 2 8-bit
+  int B, H, N, D, box_rows;
+  int64_t sB, sH, sN;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && kind == o.kind && B == o.B && H == o.H && N == o.N && D == o.D && box_rows == o.box_rows &&
+           sB == o.sB && sH == o.sH && sN == o.sN;
+  }
+};
+inline int cached_tmap_bhnd(CUtensorMap* out, const void* base, int kind, int B, int H, int N, int D, int64_t sB,
+                            int64_t sH, int64_t sN, int box_rows) {
+  constexpr int kEntries = 16;
+  struct Entry {
+    TmapKey key;
+    CUtensorMap map;
+    bool valid;
+  };
+  thread_local Entry cache[kEntries] = {};
+  thread_local int next = 0;
+  const TmapKey key{base, kind, B, H, N, D, box_rows, sB, sH, sN};
+  for (int i = 0; i < kEntries; ++i)
+    if (cache[i].valid && cache[i].key == key) {
+      *out = cache[i].map;
+      return 0;
+    }
+  const int r = kind == 2 ? make_tmap_bhnd_8bit(out, base, B, H, N, D, sB, sH, sN, box_rows)
+                          : make_tmap_bhnd_16bit(out, base, kind, B, H, N, D, sB, sH, sN, box_rows);
+  if (r == 0) {
+    cache[next] = Entry{key, *out, true};
+    next = (next + 1) % kEntries;
+  }
+  return r;
+}
+
 }  // namespace fa

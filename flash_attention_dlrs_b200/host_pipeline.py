@@ -13,12 +13,15 @@ from __future__ import annotations
 import torch
 
 from . import _native
-from .flash_attention_torch import _validate
 
 
-def _as_bh(t: torch.Tensor) -> torch.Tensor:
+def _as_bh(t: torch.Tensor, what: str) -> torch.Tensor:
+    """(B, H, N, D) -> (B*H, N, D) as a VIEW: a reshape that copies would send the device->host results into a
+    temporary (outputs) or add a hidden pageable copy (inputs), so non-contiguous or unpinned buffers are refused."""
+    if t.device.type != "cpu" or not t.is_pinned() or not t.is_contiguous():
+        raise ValueError(f"{what} must be contiguous pinned host tensors of shape (B, H, N, D)")
     B, H, N, D = t.shape
-    return t.reshape(B * H, N, D)
+    return t.view(B * H, N, D)
 
 
 class HostAttentionPipeline:
@@ -43,6 +46,7 @@ class HostAttentionPipeline:
         # double-buffered inputs, double-buffered outputs
         self.inp = [[mk() for _ in range(n_in)] for _ in range(2)]
         self.out = [[mk() for _ in range(n_out)] for _ in range(2)]
+        self.lse = [torch.empty((1, self.per, N), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device) if duplex else self.s_in
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -52,13 +56,15 @@ class HostAttentionPipeline:
 
     def run(self, host_in, host_out, causal: bool = False, softmax_scale: float = 1.0, lse_out=None):
         """host_in = (Q, K, V[, dO]) pinned (B,H,N,D) tensors; host_out = (O[, dQ, dK, dV]) pinned tensors written in
-        place.  Asynchronous with respect to the host, and the calling stream does not wait for the copies either: the
+        place; `lse_out` (optional): pinned float32 (B,H,N) or (B,H,N,1) that receives L (log2 units).  Asynchronous with respect to the host, and the calling stream does not wait for the copies either: the
         caller synchronises on the returned event (recorded after the last device->host copy) before reading
         `host_out` or rewriting `host_in`.  Calls must come from one stream (the staging buffers are ordered by events
         recorded on it)."""
         compute = torch.cuda.current_stream(self.device)
-        hin = [_as_bh(t) for t in host_in]
-        hout = [_as_bh(t) for t in host_out]
+        hin = [_as_bh(t, "host_in") for t in host_in]
+        hout = [_as_bh(t, "host_out") for t in host_out]
+        if lse_out is not None:
+            lse_v = _as_bh(lse_out.view(*lse_out.shape[:3], 1), "lse_out")[..., 0]   # (B*H, N) float32
         per, nc = self.per, self.chunks
         # ev_in_free / ev_out_free carry over from the previous call (an event never recorded does not block)
 
@@ -84,12 +90,16 @@ class HostAttentionPipeline:
                 outs += list(_native.backward(q, k, v, O, self.inp[b][3], L, causal, softmax_scale))
             for dst, src in zip(self.out[b], outs):
                 dst.copy_(src)          # device-side staging so the allocator can recycle `outs` immediately
+            if lse_out is not None:
+                self.lse[b].copy_(L)
             self.ev_in_free[b].record(compute)
             self.ev_done[b].record(compute)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_done[b])
                 for dst, src in zip(hout, self.out[b]):
                     dst[c * per:(c + 1) * per].copy_(src[0], non_blocking=True)
+                if lse_out is not None:
+                    lse_v[c * per:(c + 1) * per].copy_(self.lse[b][0], non_blocking=True)
                 self.ev_out_free[b].record(self.s_out)
         done = torch.cuda.Event()
         done.record(self.s_out)

@@ -236,9 +236,16 @@ class PeerTransport:
         return [home[c, k] for c in range(self.nb) for k in range(2)]
 
 
-def _check(Q, K, V, ops=None):
+def _check(Q, K, V, ops=None, zigzag=False, transport=None):
+    """Everything that can be refused is refused HERE, before any communication is posted: an error raised mid-ring
+    would leave the peers waiting on sends that never arrive."""
     if ops is CudaOps and Q.dtype not in (torch.float16, torch.bfloat16):
         raise TypeError(f"dtype {Q.dtype} not supported by the ring path (float16 / bfloat16 partials).")
+    if ops is CudaOps and Q.dim() == 4 and Q.shape[-1] not in (64, 128):
+        # fa_bwd_preprocess, fa_merge_partial and the attention kernels all run unpadded on the ring path
+        raise ValueError(f"the ring path runs at head sizes 64 and 128 (got d={Q.shape[-1]}); pad the shards first")
+    if transport is not None and getattr(transport, "nb", None) is not None and transport.nb != (2 if zigzag else 1):
+        raise ValueError(f"transport was built with zigzag={transport.nb == 2} but the call says zigzag={bool(zigzag)}")
     if Q.dim() != 4 or Q.shape != K.shape or Q.shape != V.shape:
         raise ValueError("Q, K, V must all be local shards of shape (B, H, n, d) with the same n on every rank")
     if Q.dtype != K.dtype or K.dtype != V.dtype:
@@ -268,7 +275,7 @@ def ring_attention_forward(Q, K, V, causal: bool = False, softmax_scale: float =
     """Local shards in, (O_local in the input dtype, L_local (B,H,n,1) float32 in log2 units) out.
     zigzag=True: the local shard is [chunk rank | chunk 2G-1-rank] of a sequence cut into 2G chunks (causal balance).
     transport: None = torch.distributed point-to-point (NcclTransport(group)); a PeerTransport = NVLink peer-memory pulls."""
-    _check(Q, K, V, ops)
+    _check(Q, K, V, ops, zigzag, transport)
     tr = transport if transport is not None else NcclTransport(group)
     r, G = tr.rank, tr.world
     B, H, n, d = Q.shape
@@ -298,7 +305,7 @@ def ring_attention_forward(Q, K, V, causal: bool = False, softmax_scale: float =
 def ring_attention_backward(Q, K, V, O, dO, L, causal: bool = False, softmax_scale: float = 1.0, group=None, ops=CudaOps,
                             zigzag: bool = False, transport=None):
     """Local shards (and the forward's O_local, L_local) in, (dQ, dK, dV) of the local shards out."""
-    _check(Q, K, V, ops)
+    _check(Q, K, V, ops, zigzag, transport)
     tr = transport if transport is not None else NcclTransport(group)
     r, G = tr.rank, tr.world
     B, H, n, d = Q.shape

@@ -69,11 +69,25 @@ class PeerGatherBuffer:
 
     def forward_into(self, Q_local, K_local, V_local, causal, softmax_scale):
         """Run this rank's forward with the fused gather; returns (gathered tensor, L_local).  The gathered tensor is
-        complete on every rank after the barrier this method issues on the current stream."""
+        complete on every rank after the barrier this method issues on the current stream.
+
+        Lifetime rule: the returned tensor is the live symmetric buffer — the NEXT call overwrites it on every rank.
+        A barrier on entry orders every rank's reads of the previous result (on its current stream) before any rank's
+        epilogue stores of this call; work queued on OTHER streams must be ordered by the caller (or use a clone).
+        Forward-only: the kernel is called below the autograd Function, the result carries no grad_fn."""
         from . import _native
 
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (Q_local, K_local, V_local)):
+            raise RuntimeError("PeerGatherBuffer.forward_into is forward-only (the gathered O has no grad_fn); "
+                               "run it under torch.no_grad() or use head_sharded_attention(gather=False) for training")
         view = self.window(self.rank)
         assert view.shape == Q_local.shape, (view.shape, Q_local.shape)
+        # write-after-read across calls: nobody may store into a peer's copy while that peer still reads the last result
+        self.handle.barrier()
+        if Q_local.numel() == 0:   # this rank owns no heads (H < world): nothing to compute, only the barriers
+            L = torch.empty(Q_local.shape[:3], dtype=torch.float32, device=Q_local.device)
+            self.handle.barrier()
+            return self.tensor, L
         off = view.data_ptr() - self.tensor.data_ptr()
         strides = tuple(view.stride())
         if self.multicast_base:
@@ -87,6 +101,22 @@ class PeerGatherBuffer:
         return self.tensor, L
 
 
+class _GatherHeads(torch.autograd.Function):
+    """all_gather_heads with a backward: every rank receives the full dO of the gathered output, and the gradient of
+    its own head slice is just that slice (each rank's loss is a function of the same gathered O; summing the ranks'
+    contributions is the caller's data-parallel reduction, exactly as with any replicated activation)."""
+
+    @staticmethod
+    def forward(ctx, local, H, group):
+        world = dist.get_world_size(group)
+        ctx.h0, ctx.h1 = head_range(H, dist.get_rank(group), world)
+        return all_gather_heads(local, H, group)
+
+    @staticmethod
+    def backward(ctx, grad_full):
+        return grad_full[:, ctx.h0:ctx.h1].contiguous(), None, None
+
+
 def head_sharded_attention(Q, K, V, causal: bool = False, softmax_scale: float = 1.0, group=None,
                            gather: bool = False, attn_fn=None):
     """Attention over this rank's head slice of replicated (B, H, N, d) inputs.
@@ -95,6 +125,10 @@ def head_sharded_attention(Q, K, V, causal: bool = False, softmax_scale: float =
     `gather=True` (NCCL all-gather after the kernel) or `gather=<PeerGatherBuffer>` (the kernel's epilogue writes every
     rank's copy itself, no collective).  The head slice is a strided view (no copy);
     `attn_fn(q, k, v, causal, softmax_scale)` defaults to FlashAttention.apply.
+
+    Gradients: the local output and `gather=True` are differentiable (the all-gather's backward hands each rank the
+    dO slice of its own heads, then the local attention backward runs); `gather=<PeerGatherBuffer>` is forward-only
+    and raises if an input requires grad while grad mode is on.
     """
     if attn_fn is None:
         from .flash_attention_torch import FlashAttention
@@ -108,4 +142,6 @@ def head_sharded_attention(Q, K, V, causal: bool = False, softmax_scale: float =
     o_local = attn_fn(Q[:, h0:h1], K[:, h0:h1], V[:, h0:h1], causal, softmax_scale)
     if not gather or world == 1:
         return o_local
+    if torch.is_grad_enabled() and o_local.requires_grad:
+        return _GatherHeads.apply(o_local, H, group)
     return all_gather_heads(o_local.detach(), H, group)

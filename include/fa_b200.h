@@ -8,7 +8,7 @@
  *   - Tensors are (B, H, N, D) with ELEMENT strides {sB, sH, sN, sD}; sD must be 1.  For 16-bit dtypes the
  *     other strides must be multiples of 8 elements and base pointers 16-byte aligned (TMA requirement).
  *   - dtype: 0 = float16, 1 = bfloat16, 2 = float32, 3 / 4 = FP8 E4M3 / E5M2 (fa_fwd only, D = 128, byte strides that are
- *     multiples of 16).   D in {64, 128} for 16-bit, D % 4 == 0 and D <= 128 for
+ *     multiples of 16).   D in {64, 128} for 16-bit, D in {16, 32, 64, 128} for
  *     float32 (the Python boundary pads other head sizes, as flash_attention_torch.py:38-47 does).
  *   - lse / delta are contiguous fp32 (B, H, N); lse is in LOG2 units: lse = log2(e) * logsumexp_j(scale*S_ij)
  *     (flash_attention_kernels.py:106).

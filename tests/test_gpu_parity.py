@@ -9,8 +9,9 @@ Tolerances (BASELINE.json north_star; reference src/test_correctness.py:40,60-62
                        one or two keys have |O| ~ |V|);
                      * P cast to the input dtype before P.V, as the reference does (flash_attention_kernels.py:98):
                        2^-(mant+2) * (P |V|)  (bf16: 2^-9 sum_j P_ij |V_jd|).
-                   The plain 2e-3 is asserted wherever it is attainable: float16 non-causal everywhere, bfloat16 on the
-                   tutorial distribution (|V| ~ 0.5).
+                   The plain 2e-3 is asserted wherever it is attainable: every non-causal case with N >= 64 — float16
+                   at any scale, bfloat16 at softmax_scale <= 1/sqrt(D) and on the tutorial distribution.  The measured
+                   maxima per BASELINE config are in profiles/r02_parity_errors.json (tools/parity_errors.py).
   gradients        max|g - g_ref| / max|g_ref| <= 1e-2
   backward         bit-identical across repeated runs
 """
@@ -81,7 +82,11 @@ def check_case(seed, B, H, N, D, dtype, causal, scale, dist="randn", strict_o=No
     else:
         bound = o_bound(Q, K, V, ref["O"], scale, causal, dtype)
         assert (o_err <= bound).all(), f"O err {o_err.max().item():.3e}"
-        if strict_o if strict_o is not None else (not causal and (dtype == torch.float16 or dist == "tutorial")):
+        # the north-star's plain 2e-3 wherever it is attainable: every non-causal case at a softmax scale <= 1/sqrt(D)
+        # (rows average over many keys, |O| < 1), float16 and bfloat16 alike (the bf16
+        # quantisation floor there is 1.0e-3); causal rows that see one or two keys have |O| ~ |V| and keep `bound`
+        attainable = not causal and N >= 64 and (dtype == torch.float16 or scale * math.sqrt(D) <= 1.05 or dist == "tutorial")
+        if strict_o if strict_o is not None else attainable:
             assert o_err.max().item() <= 2e-3, f"O err {o_err.max().item():.3e} (strict)"
         assert l_err <= 2e-3, f"L err {l_err:.3e}"
     for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
@@ -599,6 +604,43 @@ def test_reference_gradcheck_script_runs_unmodified(capsys):
     assert "Deterministic backwards test successful" in out, out
 
 
+def test_reference_correctness_script_runs_unmodified(capsys):
+    """src/test_correctness.py of the reference, byte for byte (baseline/_ref/src): 200 seeds x (forward, dQ, dK, dV with
+    deterministic=False, dQ, dK, dV with deterministic=True) against torch SDPA + autograd at the reference's own
+    tolerances (test_correctness.py:28-76).  Only sys.path decides that `flash_attention_wrappers` is this package's
+    compat shim; every one of the seven summary lines must read 200 out of 200."""
+    import hashlib
+    import runpy
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "baseline", "_ref", "src", "test_correctness.py")
+    if not os.path.exists(script):
+        pytest.skip("baseline/_ref/src not present (tools/fetch_reference.sh)")
+    assert hashlib.sha1(open(script, "rb").read()).hexdigest() == "2fbd97fea76fb687e152a580e04fa8359d08e34c"
+    compat = os.path.join(root, "flash_attention_dlrs_b200", "compat")
+    sys.path.insert(0, compat)
+    for mod in ("flash_attention_wrappers", "flash_attention_torch"):   # a stale import must not decide the module
+        sys.modules.pop(mod, None)
+    try:
+        runpy.run_path(script, run_name="__main__")
+        import flash_attention_wrappers as w
+        assert os.path.dirname(os.path.abspath(w.__file__)) == compat, w.__file__
+    finally:
+        sys.path.remove(compat)
+    out = capsys.readouterr().out
+    for what in ("forward", "Q backward", "K backward", "V backward", "Q deterministic backward",
+                 "K deterministic backward", "V deterministic backward"):
+        assert f"200 out of 200 {what} tests succeeded!" in out, out
+
+
+def _free_port():
+    """A TCP port nobody listens on right now (fixed ports collide when two test runs share a box)."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _run_peer_gather(nproc, port):
     import json
     import subprocess
@@ -619,14 +661,14 @@ def _run_peer_gather(nproc, port):
 def test_fused_gather_epilogue_single_rank():
     """PeerGatherBuffer end to end with one rank (torchrun, symmetric-memory rendezvous, kernel writing O in place at
     the buffer's address, barrier): equals the plain forward bit for bit."""
-    _run_peer_gather(1, 29916)
+    _run_peer_gather(1, _free_port())
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box")
 def test_fused_gather_epilogue_matches_nccl_all_gather_two_gpus():
     """Two ranks (torchrun, NCCL for the rendezvous and the comparison path): the gathered O written by the forward
     kernels' epilogues (NVLS multicast and / or P2P stores) equals forward + NCCL all-gather bit for bit."""
-    _run_peer_gather(2, 29917)
+    _run_peer_gather(2, _free_port())
 
 
 # ------------------------------------------------------------------------------------------------ key-padding mask
@@ -762,7 +804,7 @@ def test_ring_attention_two_gpus():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29919", os.path.join(root, "tools", "multi_gpu_ring.py"), "1", "4", "2048", "128"]
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(root, "tools", "multi_gpu_ring.py"), "1", "4", "2048", "128"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]

@@ -32,6 +32,18 @@ def _worker(rank, world, port, B, H, ok):
         good = local.shape[1] == h1 - h0 and torch.allclose(local, full[:, h0:h1], atol=1e-6)
         gathered = head_sharded_attention(Q, K, V, True, 0.25, gather=True, attn_fn=fn)
         good = good and gathered.shape == full.shape and torch.allclose(gathered, full, atol=1e-6)
+        # training through the gathered output: every rank gets the gradients of ITS head slice of the replicated inputs
+        Qg, Kg, Vg = (t.clone().requires_grad_(True) for t in (Q, K, V))
+        w = torch.randn(full.shape, generator=torch.Generator().manual_seed(5))
+        out = head_sharded_attention(Qg, Kg, Vg, True, 0.25, gather=True, attn_fn=fn)
+        good = good and out.requires_grad
+        (out * w).sum().backward()
+        Qr, Kr, Vr = (t.clone().requires_grad_(True) for t in (Q, K, V))
+        (orc.reference_sdpa(Qr, Kr, Vr, 0.25, True) * w).sum().backward()
+        for got, ref in ((Qg.grad, Qr.grad), (Kg.grad, Kr.grad), (Vg.grad, Vr.grad)):
+            good = good and torch.allclose(got[:, h0:h1], ref[:, h0:h1], atol=1e-5)
+            rest = torch.cat([got[:, :h0], got[:, h1:]], dim=1)
+            good = good and not rest.any()          # other ranks' heads: no gradient on this rank
         ok[rank] = 1 if good else 0
     finally:
         dist.destroy_process_group()
