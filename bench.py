@@ -233,11 +233,134 @@ def run_reference_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ host placement
+def bind_to_gpu_numa_node(local_rank: int):
+    """Bind this process (and therefore its pinned allocations, first touch) to the NUMA node of its GPU: with 8 ranks
+    pinning 1 GiB each from whatever core they start on, half of the PCIe traffic otherwise crosses the socket link.
+    Returns a short description for the bench line; never raises."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return f"gpu {bdf}: no NUMA node reported"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"gpu {bdf}: node {node} has no allowed cpu"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {bdf} -> node {node}, {len(allowed)} cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
+def bare_pcie_each_way(dev, host_in, host_out, barrier):
+    """GB/s each way of bare simultaneous cudaMemcpyAsync H2D + D2H of the step's bytes (the same pinned buffers, 64 MiB
+    pieces on two streams), all ranks copying at the same time: the ceiling the host pipeline can be held against."""
+    nbytes = sum(t.numel() * t.element_size() for t in host_in)
+    d_in = [torch.empty_like(t, device=dev) for t in host_in]
+    d_out = [torch.ones_like(t, device=dev) for t in host_out]
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    piece = 8   # heads per copy: 8 x 8192 x 128 x 2 B = 16 MiB
+
+    def both():
+        cur = torch.cuda.current_stream()
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        for hi, di, ho, do_ in zip(host_in, d_in, host_out, d_out):
+            for h in range(0, hi.shape[1], piece):
+                with torch.cuda.stream(s1):
+                    di[:, h:h + piece].copy_(hi[:, h:h + piece], non_blocking=True)
+                with torch.cuda.stream(s2):
+                    ho[:, h:h + piece].copy_(do_[:, h:h + piece], non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+
+    both()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        both()
+    b.record()
+    barrier()
+    return nbytes / (a.elapsed_time(b) / 3 * 1e-3) / 1e9
+
+
+def c4_strong(world, rank, dev, barrier):
+    """BASELINE configs[3] — fwd+bwd bf16 B=1 H=64 N=32768 D=128 causal, head-sharded (STRONG scaling: the job is fixed,
+    rank g owns heads [g*64/G, (g+1)*64/G)), no collective on the compute path.  Returns the record for the bench line:
+    step ms (max over ranks), whole-job TFLOP/s, a fingerprint of all 64 heads' outputs (inputs are seeded per head, so it
+    must be the same for every G), and the optional NCCL all-gather of O timed on its own."""
+    import hashlib
+
+    import torch.distributed as dist
+
+    from flash_attention_dlrs_b200 import flash_attention_backward, flash_attention_forward, sharding
+
+    B, H, N, D = 1, 64, 32768, 128
+    scale = D ** -0.5
+    h0, h1 = sharding.head_range(H, rank, world)
+    hl = h1 - h0
+
+    def make(kind):
+        out = torch.empty(B, hl, N, D, dtype=torch.bfloat16, device=dev)
+        for i, h in enumerate(range(h0, h1)):
+            g = torch.Generator(device=dev).manual_seed(1000 * h + kind)
+            out[:, i] = torch.randn(B, N, D, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+        return out
+
+    Q, K, V, dO = (make(k) for k in range(4))
+
+    def step():
+        O, L = flash_attention_forward(Q, K, V, dev, True, scale)
+        return O, flash_attention_backward(Q, K, V, O, dO, L, dev, True, True, scale)
+
+    step()
+    barrier()
+    steps = 3
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        O, (dQ, dK, dV) = step()
+    b.record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+    gather_ms = None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sharding.all_gather_heads(O, H)
+        barrier()
+        a.record()
+        sharding.all_gather_heads(O, H)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = t.item()
+    fp = torch.stack([torch.stack([t[:, i].contiguous().view(torch.int16).to(torch.int64).sum() for t in (O, dQ, dK, dV)])
+                      for i in range(hl)])
+    if world > 1:
+        parts = [torch.zeros_like(fp) for _ in range(world)]
+        dist.all_gather(parts, fp)      # H % world == 0 for 1 / 2 / 4 / 8 ranks
+        fp = torch.cat(parts)
+    fl = flops(B, H, N, D, True, "fwd_bwd")
+    return {"config": "BASELINE configs[3]: fwd+bwd bf16 B=1 H=64 N=32768 D=128 causal, head-sharded", "scaling": "strong",
+            "n_gpus": world, "heads_per_gpu": hl, "ms_per_step": ms.item(), "tflops": fl / (ms.item() * 1e-3) / 1e12,
+            "allgather_O_ms": gather_ms, "allgather_bytes_per_rank": B * hl * N * D * 2,
+            "fingerprint_O_dQ_dK_dV": hashlib.sha256(fp.cpu().numpy().tobytes()).hexdigest()[:16]}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch.distributed as dist
 
-    from flash_attention_dlrs_b200 import FlashAttention, _lib, _native
+    from flash_attention_dlrs_b200 import _lib, _native, flash_attention_backward, flash_attention_forward
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +369,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank)     # before any pinned allocation (first touch decides the node)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -260,8 +384,9 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step():
-        O, L = _native.forward(Q, K, V, causal, scale)
-        return O, _native.backward(Q, K, V, O, dO, L, causal, scale)
+        # the reference-facing entry points (flash_attention_wrappers.py:7-12,66-75), not the internals under them
+        O, L = flash_attention_forward(Q, K, V, dev, causal, scale)
+        return O, flash_attention_backward(Q, K, V, O, dO, L, dev, True, causal, scale)
 
     def barrier():
         if world > 1:
@@ -384,11 +509,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = t.item()
     io_bytes = 4 * B * H * N * D * 2
+    bare = bare_pcie_each_way(dev, host, out_host, barrier)
+    if world > 1:
+        t = torch.tensor([bare], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        bare = t.item()
     e2e = {"value": job_flops / (e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e_ms,
            "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
            "api": "HostAttentionPipeline.run((Q,K,V,dO) pinned host -> (O,dQ,dK,dV) pinned host), %d head chunks, "
                   "copies overlapped with the kernels and consecutive steps pipelined, duplex=%s" % (chunks_used, duplex_used),
-           "pcie_gbs_each_way": io_bytes / (e_ms * 1e-3) / 1e9}
+           "pcie_gbs_each_way": io_bytes / (e_ms * 1e-3) / 1e9,
+           "pcie_bare_gbs_each_way": bare,
+           "pcie_bare_note": "bare simultaneous H2D + D2H cudaMemcpyAsync of the same pinned buffers per GPU, all ranks at "
+                             "once (slowest rank): the pipeline's ceiling on this box at this N",
+           "host_numa": numa}
+    del pipe
+    torch.cuda.empty_cache()
+    c4 = c4_strong(world, rank, dev, barrier)
 
     if rank == 0:
         # on rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1 on multi-rank launches; the N = 1 line carries it)
@@ -405,7 +542,10 @@ def run_ours(args):
             "frac_of_bf16_peak_note": "per-GPU value / sustained bf16 peak (" + peaks["source"] + ")",
             "frac_of_bf16_burst_peak": value / world / peaks["burst"],
             "fwd_tflops": kernels["fwd"]["alg_tflops"], "fwd_frac_of_bf16_burst_peak": kernels["fwd"]["alg_tflops"] / peaks["burst"],
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels,
+            "kernels_note": "each kernel timed alone in its own loop (hotter than inside the mixed step: the sum of the "
+                            "four can exceed ms_per_step by a few percent)",
+            "cpu_baseline": cpu, "e2e": e2e, "c4_strong": c4,
             "gpu_launches": 4 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

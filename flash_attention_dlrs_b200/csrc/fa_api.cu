@@ -288,6 +288,12 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   if (band) p.band = 1, p.win_left = mask->window_left, p.win_right = mask->window_right;
   if (mask && mask->blocks)
     p.ablock = mask->blocks, p.ab_sB = mask->blocks_strides[0], p.ab_sH = mask->blocks_strides[1], p.ab_sI = mask->blocks_strides[2];
+  if (fa_host::fwd_pair_eligible(dtype, D, p)) {
+    CUtensorMap tk64;
+    if (int r = fa::cached_tmap_bhnd(&tk64, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 64))
+      return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k, 64-row box) failed (%d)", r);
+    return fa_host::launch_fwd16_pair(dtype, D, causal != 0, tq, tk64, tv, p, H, B, st);
+  }
   return fa_host::launch_fwd16(dtype, D, causal != 0, tq, tk, tv, p, H, B, st);
 }
 

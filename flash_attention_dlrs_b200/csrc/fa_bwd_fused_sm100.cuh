@@ -41,6 +41,18 @@
 #ifndef FA_FUSED_PACE
 #define FA_FUSED_PACE 40
 #endif
+// FA_FUSED_ABLATE 3 (timing experiment, wrong results): unordered and only half of every dQ partial leaves the SM.
+// FA_FUSED_TURN_WARPS: 1 = the turn-taking of the ordered dQ reduction runs on two otherwise idle warps (warp 14 polls
+// the turn counter, warp 15 publishes the next turn) instead of on the reducer warps, so that neither the poll's L2 round
+// trip nor the release's wait for the drain of ~64 KiB of reductions ever blocks the warps that feed the SM -> L2 path;
+// 0 = the round-1 protocol (every reducer thread fences, thread 0 polls and releases).
+#ifndef FA_FUSED_TURN_WARPS
+#define FA_FUSED_TURN_WARPS 1
+#endif
+#ifndef FA_FUSED_HALF
+#define FA_FUSED_HALF (FA_FUSED_ABLATE == 3 || FA_FUSED_ABLATE == 4)
+#endif
+#define FA_FUSED_UNORDERED (FA_FUSED_ABLATE == 1 || FA_FUSED_ABLATE == 2 || FA_FUSED_ABLATE == 3)
 
 namespace fa {
 
@@ -200,8 +212,11 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* ds_free = bars + 12;
   uint64_t* dq_full = bars + 13;
   uint64_t* dq_free = bars + 14;
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 18);
-  int* ticket_s = reinterpret_cast<int*>(bars + 19);
+  uint64_t* turn_ok = bars + 15;      // [2] warp 14 -> reducer: it is this CTA's turn on the tile of visit v
+  uint64_t* reds_out = bars + 17;     // [2] reducer -> warps 14 / 15: the reductions of visit v have been issued
+  uint64_t* rel_done = bars + 19;     // [2] warp 15 -> reducer: the turn of visit v has been passed on
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 22);
+  int* ticket_s = reinterpret_cast<int*>(bars + 23);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,6 +244,11 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(ds_free, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 128);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&turn_ok[t], 1);
+      mbar_init(&reds_out[t], 128);
+      mbar_init(&rel_done[t], 1);
+    }
     fence_mbar_init();
     // Tickets are handed out in launch order: a CTA's predecessor in the dQ reduction always holds a smaller ticket.
     *ticket_s = atomicAdd(fp.ticket, 1);
@@ -405,6 +425,43 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     }
+#if FA_FUSED_TURN_WARPS && !FA_FUSED_UNORDERED
+    else if (lane == 0) {
+      // ------------------------------------------------------------------ turn warps (14: acquire, 15: release)
+      const int64_t tiles_bh = (int64_t)bh * n;
+      for (int v = 0; v < n_vis; ++v) {
+        const int i = q_block(v);
+        const bool buf_b = !kCausal && i < jb;
+        const int rank = buf_b ? n - 1 - jb : v;
+        int* sem = fp.sem + (buf_b ? (int64_t)p.B * p.H * n : 0) + tiles_bh + i;
+        if (warp == 14) {
+          // slot v & 1 of turn_ok is free once the reducer has passed visit v - 2 (it waited on it before its reductions)
+          if (v >= 2) mbar_wait(&reds_out[v & 1], ((v - 2) >> 1) & 1);
+          if (rank != 0) {
+#if FA_WATCHDOG
+            long long t0 = clock64();
+#endif
+            while (ld_acquire_gpu(sem) != rank) {
+#if FA_WATCHDOG
+              if (clock64() - t0 > FA_WATCHDOG_CYCLES) {
+                printf("[fa watchdog] dQ turn wait timed out: ticket %d bh %d j %d i %d rank %d sem %d\n", ticket, bh, jb,
+                       i, rank, ld_acquire_gpu(sem));
+                __trap();
+              }
+#endif
+            }
+          }
+          mbar_arrive(&turn_ok[v & 1]);
+        } else {
+          // every reducer thread arrived (release, CTA scope) after issuing its reductions; the gpu-scope release below
+          // is cumulative over them: the next contributor's acquire of `rank + 1` orders its reductions after ours
+          mbar_wait(&reds_out[v & 1], (v >> 1) & 1);
+          st_release_gpu(sem, rank + 1);
+          mbar_arrive(&rel_done[v & 1]);
+        }
+      }
+    }
+#endif
   } else if (warp >= 8) {
     setmaxnreg_inc<160>();
     // ------------------------------------------------------------------ dQ reducer (warps 8-11)
@@ -433,7 +490,9 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(dq_free);
       if (rt == 0) fa_trace(3, v, 2);
-#if FA_FUSED_ABLATE != 1 && FA_FUSED_ABLATE != 2
+#if FA_FUSED_TURN_WARPS && !FA_FUSED_UNORDERED
+      mbar_wait(&turn_ok[v & 1], (v >> 1) & 1);
+#elif !FA_FUSED_UNORDERED
       if (!first) {
         if (rt == 0) {
 #if FA_WATCHDOG
@@ -453,23 +512,29 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
 #endif
 #if FA_FUSED_ABLATE != 2
+      constexpr int kOutVec = FA_FUSED_HALF ? kD / 8 : kD / 4;   // 16-byte vectors of the row that leave the SM
       // Paced: a burst of 64 KiB would monopolise the SM's path to L2 (~25 B/clk) and hold up the TMA requests of the
       // next Q / dO tiles; one 512-byte warp instruction every FA_FUSED_PACE ns per warp keeps the path shared.
       if (first) {
 #pragma unroll
-        for (int k = 0; k < kD / 4; ++k) {
+        for (int k = 0; k < kOutVec; ++k) {
           st_f32x4(tile + k * 512, r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
           if (FA_FUSED_PACE) __nanosleep(FA_FUSED_PACE);
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < kD / 4; ++k) {
+        for (int k = 0; k < kOutVec; ++k) {
           red_add_f32x4(tile + k * 512, r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
           if (FA_FUSED_PACE) __nanosleep(FA_FUSED_PACE);
         }
       }
 #endif
-#if FA_FUSED_ABLATE != 1 && FA_FUSED_ABLATE != 2
+#if FA_FUSED_TURN_WARPS && !FA_FUSED_UNORDERED
+      // the turn is passed on by warp 15 once all 128 reducer threads have issued their reductions; slot v & 1 of
+      // reds_out is reusable because warp 15 has consumed visit v - 2 (rel_done)
+      if (v >= 2) mbar_wait(&rel_done[v & 1], ((v - 2) >> 1) & 1);
+      mbar_arrive(&reds_out[v & 1]);
+#elif !FA_FUSED_UNORDERED
       __threadfence();
       named_bar_sync(1, 128);
       if (rt == 0) st_release_gpu(sem, rank + 1);

@@ -44,6 +44,11 @@ int set_smem_once(K kernel, int bytes, std::atomic<uint64_t>& done) {
 // tcgen05 forward (fa_launch_fwd.cu).  elt: 0 f16, 1 bf16, 3 e4m3, 4 e5m2; dropout / mask variants chosen from p.
 int launch_fwd16(int elt, int D, bool causal, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                  const fa::FwdParams& p, int H, int B, cudaStream_t st);
+// CTA-pair forward (fa_fwd2_sm100.cuh): true when the problem runs on it (16-bit, D = 128, no dropout / mask)
+bool fwd_pair_eligible(int elt, int D, const fa::FwdParams& p);
+// tk64: K with a 64-row box (each CTA of a pair loads half of every key block)
+int launch_fwd16_pair(int elt, int D, bool causal, const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv,
+                      const fa::FwdParams& p, int H, int B, cudaStream_t st);
 // tcgen05 backward, one kernel each (fa_launch_dkdv.cu, fa_launch_dq.cu)
 int launch_bwd16_dkdv(bool bf16, int D, bool causal, const fa::BwdMaps& m, const fa::BwdParams& p, cudaStream_t st);
 int launch_bwd16_dq(bool bf16, int D, bool causal, const fa::BwdMaps& m, const fa::BwdParams& p, cudaStream_t st);

@@ -1,7 +1,14 @@
 // fa_launch_fwd.cu — instantiations and launch dispatch of the tcgen05 forward kernel (own translation unit: see fa_host.h).
 #include "../../include/fa_b200.h"
+#include "fa_fwd2_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
+
+#include <cstdlib>
 #include "fa_host.h"
+
+#ifndef FA_FWD_PAIR_DEFAULT
+#define FA_FWD_PAIR_DEFAULT 0
+#endif
 
 namespace {
 
@@ -24,7 +31,42 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   return e == cudaSuccess ? 0 : fa_host::cuda_fail(e, "fa_fwd launch");
 }
 
+template <bool kBf16, int kD, bool kCausal>
+int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv, fa::FwdParams p, int H, int B,
+                cudaStream_t st) {
+  using Cfg = fa::Fwd2Cfg<kD>;
+  auto kern = fa::fa_fwd2_kernel<kBf16, kD, kCausal>;
+  static std::atomic<uint64_t> smem_set{0};
+  if (int r = fa_host::set_smem_once(kern, Cfg::kSmemBytes, smem_set)) return r;
+  p.q_blocks = (p.N + 511) / 512;   // 512-row quads: one per CTA pair (the cluster dimension is compiled in)
+  dim3 grid(2 * p.q_blocks, H, B);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk64, tv, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fa_host::cuda_fail(e, "fa_fwd (CTA pairs) launch");
+}
+
 }  // namespace
+
+// FA_FWD_PAIR = 0 / 1 overrides the default choice between the single-CTA and the CTA-pair forward (A/B measurements).
+bool fa_host::fwd_pair_eligible(int elt, int D, const fa::FwdParams& p) {
+  static const int mode = [] {
+    const char* e = std::getenv("FA_FWD_PAIR");
+    return e ? std::atoi(e) : FA_FWD_PAIR_DEFAULT;
+  }();
+  return mode != 0 && (elt == FA_DTYPE_F16 || elt == FA_DTYPE_BF16) && D == 128 && !p.drop.thresh && !p.amask && !p.band;
+}
+
+int fa_host::launch_fwd16_pair(int elt, int D, bool causal, const CUtensorMap& tq, const CUtensorMap& tk64,
+                               const CUtensorMap& tv, const fa::FwdParams& p, int H, int B, cudaStream_t st) {
+  const bool bf = elt == FA_DTYPE_BF16;
+  if (D == 128) {
+    if (bf && causal) return launch_pair<true, 128, true>(tq, tk64, tv, p, H, B, st);
+    if (bf && !causal) return launch_pair<true, 128, false>(tq, tk64, tv, p, H, B, st);
+    if (!bf && causal) return launch_pair<false, 128, true>(tq, tk64, tv, p, H, B, st);
+    return launch_pair<false, 128, false>(tq, tk64, tv, p, H, B, st);
+  }
+  return fa_host::fail(-3, "fa_fwd: no CTA-pair kernel for D %d", D);
+}
 
 int fa_host::launch_fwd16(int elt, int D, bool causal, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           const fa::FwdParams& p, int H, int B, cudaStream_t st) {

@@ -184,6 +184,61 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2): one MMA stream issued by the leader CTA (cluster rank 0)
+// computes M = 256 rows, 128 per CTA, each CTA supplying its own A rows and HALF of the B operand (N split) — the pair
+// reads every B tile from shared memory once instead of twice.  Validated on hardware by tools/umma2_probe.cu.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// arrive (release, cluster scope) on an mbarrier given by its shared::cluster address (possibly in the other CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {  // one full warp, the same warp index in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// TMA load into THIS CTA's shared memory; the completion bytes are signalled on the mbarrier at cluster address
+// `mbar_cluster` (the leader's barrier: the MMA issuer waits for both CTAs' halves on one barrier)
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit2(uint64_t* bar, uint16_t mask = 3) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // UMMA descriptors
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version bits.
@@ -301,6 +356,45 @@ __device__ __forceinline__ void umma_ts_off(uint32_t tmem_d, uint32_t tmem_a_bas
       "add.u32 bl, %2, %7;\n\t"
       "mov.b64 db, {bl, %5};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA),
+        "n"(kOffB)
+      : "memory");
+}
+// cta_group::2 variants (issued by the leader CTA only; descriptors / TMEM addresses are the same offsets in both CTAs)
+template <uint32_t kOffA, uint32_t kOffB>
+__device__ __forceinline__ void umma2_ss_off(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 al, %1, %6;\n\t"
+      "add.u32 bl, %2, %7;\n\t"
+      "mov.b64 da, {al, %5};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA), "n"(kOffB)
+      : "memory");
+}
+template <uint32_t kOffA, uint32_t kOffB>
+__device__ __forceinline__ void umma2_ts_off(uint32_t tmem_d, uint32_t tmem_a_base, uint32_t b_base, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 ta, bl;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 ta, %1, %6;\n\t"
+      "add.u32 bl, %2, %7;\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [ta], db, %3, p;\n\t"
       "}\n"
       :
       : "r"(tmem_d), "r"(tmem_a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA),
