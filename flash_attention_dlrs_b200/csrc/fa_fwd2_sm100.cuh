@@ -25,6 +25,19 @@
 
 namespace fa {
 
+// FA_TRACE builds: the heaviest pair of head (0, 0) records clock64 per role / block / event (role = 3 * rank + {0: MMA
+// thread, 1: softmax slot 0, 2: softmax slot 1}); clocks of the two SMs are not comparable with each other.
+#if FA_TRACE
+__device__ __forceinline__ void fa_trace2(int role, int it, int k) {
+  if (g_fa_trace != nullptr && (blockIdx.x >> 1) == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    const int slot = (role + 3 * (int)(blockIdx.x & 1)) * 8192 + it * 8 + k;
+    if (slot < g_fa_trace_cap) g_fa_trace[slot] = clock64();
+  }
+}
+#else
+__device__ __forceinline__ void fa_trace2(int, int, int) {}
+#endif
+
 template <int kD>
 struct Fwd2Cfg {
   static_assert(kD == 128, "the CTA-pair forward is instantiated for D = 128");
@@ -175,13 +188,16 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(&v_full[s], (j / NS) & 1);
           const uint32_t dO_t = tO(t), aP = tS(t), bV = vlo + s * kVLo;
           const bool acc0 = j > 0;
+          fa_trace2(0, j, 4 * t);
           mbar_wait(&p_full[t][0], j & 1);   // P arrives in two 64-key halves (both CTAs)
+          fa_trace2(0, j, 4 * t + 1);
           tc_fence_after();
           static_for<0, 4>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             umma2_ts_off<k * 8, umma_koff_mnmajor(k)>(dO_t, aP, bV, idesc_o, acc0 || (k > 0));
           });
           mbar_wait(&p_full[t][1], j & 1);
+          fa_trace2(0, j, 4 * t + 2);
           tc_fence_after();
           static_for<4, 8>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
@@ -191,6 +207,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const bool last_user = (t == 1) || (nkv_slot[1] <= j);
           if (last_user) tc_commit2(&v_empty[s]);
           if (j + 1 < nkv_slot[t]) issue_s(t, j + 1);
+          fa_trace2(0, j, 4 * t + 3);
         }
       }
     }
@@ -218,8 +235,11 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     };
 
     float m_used = -INFINITY, l = 0.f;
+    const bool tr = (threadIdx.x & 127) == 0;
     for (int j = 0; j < my_slot; ++j) {
+      if (tr) fa_trace2(1 + t, j, 0);
       mbar_wait(&s_full[t], j & 1);
+      if (tr) fa_trace2(1 + t, j, 1);
       tc_fence_after();
       if (j >= my_own) {
         // The pair's other tile still needs this key block; for this tile it is entirely above the diagonal (or the tile
@@ -301,13 +321,17 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           pk[i] = pack2<kBf16>(p0, p1);
         }
         tmem_st_x16(tS + c * 16, pk);
-        if (c == 1) p_arrive(pbar0);
+        if (c == 1) {
+          p_arrive(pbar0);
+          if (tr) fa_trace2(1 + t, j, 2);
+        }
       }
       float la, lb, lc, ld;
       f32x2_unpack(f32x2_add(ls[0], ls[1]), la, lb);
       f32x2_unpack(f32x2_add(ls[2], ls[3]), lc, ld);
       l += (la + lb) + (lc + ld);
       p_arrive(pbar1);
+      if (tr) fa_trace2(1 + t, j, 3);
     }
 
     if (my_slot > 0) {

@@ -269,7 +269,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             constexpr int kPSteps = kF8 ? 4 : 8, kVStep = kF8 ? 2 : 1;
             const int c = kAmask ? n_pv[t] : j;   // this tile's count of visible blocks so far
             const bool acc0 = c > 0;
+            fa_trace(0, u, 4 * t);
             mbar_wait(&p_full[t][0], c & 1);
+            fa_trace(0, u, 4 * t + 1);
             tc_fence_after();
             static_for<0, kPSteps / 2>([&](auto kc) {
               constexpr int k = decltype(kc)::value;
@@ -279,6 +281,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 umma_ts_off<k * 8, umma_koff_mnmajor(k * kVStep)>(dO_t, aP, bV, idesc_o, acc0 || (k > 0));
             });
             mbar_wait(&p_full[t][1], c & 1);
+            fa_trace(0, u, 4 * t + 2);
             tc_fence_after();
             static_for<kPSteps / 2, kPSteps>([&](auto kc) {
               constexpr int k = decltype(kc)::value;
@@ -293,6 +296,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const bool last_user = (t == 1) || (nkv[1] <= j);
           if (last_user) tc_commit(&v_empty[s]);
           if (kAmask ? (u + 1 < n_list && jn < nkv[t]) : (j + 1 < nkv[t])) issue_s(t, u + 1);
+          fa_trace(0, u, 4 * t + 3);
         }
       }
     }
@@ -336,7 +340,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (partial && am_row) mk = __ldg(reinterpret_cast<const uint4*>(am_row + j * 16));
       }
       const int c = kAmask ? n_seen : j;
+      if ((threadIdx.x & 127) == 0) fa_trace(1 + t, u, 0);
       mbar_wait(&s_full[t], c & 1);
+      if ((threadIdx.x & 127) == 0) fa_trace(1 + t, u, 1);
       tc_fence_after();
 #if FA_ABLATE == 3
       tc_fence_before();
@@ -447,6 +453,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(&p_full[t][0]);
+            if ((threadIdx.x & 127) == 0) fa_trace(1 + t, u, 2);
           }
         }
       } else {
@@ -489,6 +496,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[t][1]);
+      if ((threadIdx.x & 127) == 0) fa_trace(1 + t, u, 3);
     }
 
     if (my_nkv > 0) {

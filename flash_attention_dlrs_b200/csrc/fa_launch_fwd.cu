@@ -47,6 +47,16 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
 
 }  // namespace
 
+#if FA_TRACE
+// debug builds only: every translation unit has its own copy of the trace pointer (sm100_ptx.cuh)
+extern "C" int fa_debug_set_trace_fwd(void* dev_buf, int capacity_events) {
+  long long* p = static_cast<long long*>(dev_buf);
+  cudaMemcpyToSymbol(fa::g_fa_trace, &p, sizeof(p));
+  cudaMemcpyToSymbol(fa::g_fa_trace_cap, &capacity_events, sizeof(int));
+  return 0;
+}
+#endif
+
 // FA_FWD_PAIR = 0 / 1 overrides the default choice between the single-CTA and the CTA-pair forward (A/B measurements).
 bool fa_host::fwd_pair_eligible(int elt, int D, const fa::FwdParams& p) {
   static const int mode = [] {

@@ -26,41 +26,8 @@
 
 using namespace fa;
 
-// ------------------------------------------------------------------------------------------------ cluster / 2-CTA PTX
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-  return r;
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// TMA load into THIS CTA's shared memory, completion bytes on the mbarrier at cluster address `mbar_cluster`
-__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster, int c0, int c1,
-                                                int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
+// ------------------------------------------------------------------------------------------------ 2-CTA MMA (plain descriptors)
+// (cluster helpers, cta_group::2 TMEM allocation, the leader-barrier TMA form and the multicast commit: sm100_ptx.cuh)
 __device__ __forceinline__ void umma2_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -75,14 +42,6 @@ __device__ __forceinline__ void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint6
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
-// all prior MMAs of this thread -> arrive on the barrier at the same offset in every CTA of `mask`
-__device__ __forceinline__ void tc_commit2(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------ part 1: semantics
 struct P1 {
   int pv;   // 0: case S, 1: case PV
@@ -176,10 +135,17 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------ part 2: throughput
-// mode 0: 1-CTA SS   1: 1-CTA TS   2: 1-CTA SS + TMA fill   3: 1-CTA TS + TMA fill   4: 2-CTA SS   5: 2-CTA SS + TMA fill
-template <bool kPair>
+// kMode 0: 1-CTA SS   1: 1-CTA TS   2: 2-CTA SS   3: 2-CTA TS   (K-major B, the score product)
+//       4: 1-CTA TS with MN-major B   5: 2-CTA TS with MN-major B   (the P.V product);   fill: concurrent TMA stream.
+// The issue loop is what the attention kernels use: descriptor low words in uniform registers + compile-time offsets
+// (umma*_off), no branches — a loop with run-time branches per MMA is issue-bound (~100 clk per instruction) and says
+// nothing about the operand path.
+template <int kMode>
 __global__ void __launch_bounds__(128, 1)
-rate_kernel(const __grid_constant__ CUtensorMap tmFill, int mode, int iters, long long* out) {
+rate_kernel(const __grid_constant__ CUtensorMap tmFill, int fill, int iters, long long* out) {
+  constexpr bool kPair = kMode == 2 || kMode == 3 || kMode == 5;
+  constexpr bool kTs = kMode == 1 || kMode == 3 || kMode >= 4;
+  constexpr bool kBmn = kMode >= 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;             // 32 KiB
@@ -205,22 +171,26 @@ rate_kernel(const __grid_constant__ CUtensorMap tmFill, int mode, int iters, lon
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const bool ts = (mode == 1 || mode == 3), fill = (mode == 2 || mode == 3 || mode == 5);
 
   if (warp == 0 && rank == 0) {
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(1, kPair ? 256 : 128, 128, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(1, kPair ? 256 : 128, 128, 0, kBmn ? 1 : 0);
+      constexpr int kBBox = kPair ? 8192 : 16384;
+      const uint32_t a_lo = umma_lo_kmajor(smem_u32(sA));
+      const uint32_t b_lo = kBmn ? umma_lo_mnmajor(smem_u32(sB), 16384) : umma_lo_kmajor(smem_u32(sB));
+      const uint32_t tA = tmem + 256;
       const long long t0 = clock64();
       for (int it = 0; it < iters; ++it) {
         const uint32_t d = tmem + (it & 1) * 128;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = umma_desc_kmajor(smem_u32(sA) + (k / 4) * 16384, k % 4);
-          const uint64_t db = umma_desc_kmajor(smem_u32(sB) + (k / 4) * (kPair ? 8192 : 16384), k % 4);
-          if (kPair) umma2_ss(d, da, db, idesc, k > 0);
-          else if (ts) umma_ts(d, tmem + 256 + k * 8, db, idesc, k > 0);
-          else umma_ss(d, da, db, idesc, k > 0);
-        }
+        static_for<0, 8>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr uint32_t offA = umma_koff_kmajor(k, 16384);
+          constexpr uint32_t offB = kBmn ? umma_koff_mnmajor(k) : umma_koff_kmajor(k, kBBox);
+          if constexpr (kPair && kTs) umma2_ts_off<k * 8, offB>(d, tA, b_lo, idesc, k > 0);
+          else if constexpr (kPair) umma2_ss_off<offA, offB>(d, a_lo, b_lo, idesc, k > 0);
+          else if constexpr (kTs) umma_ts_off<k * 8, offB>(d, tA, b_lo, idesc, k > 0);
+          else umma_ss_off<offA, offB>(d, a_lo, b_lo, idesc, k > 0);
+        });
       }
       if (kPair) tc_commit2(&bar_mma, 3); else tc_commit(&bar_mma);
       mbar_wait(&bar_mma, 0);
@@ -360,7 +330,8 @@ static int run_pair(int pv) {
   return maxerr < 1e-2 ? 0 : 1;
 }
 
-static void run_rate(int mode, const char* name, int grid) {
+template <int kMode>
+static void run_rate(int fill, const char* name, int grid) {
   uint16_t* dF;
   long long* dOut;
   CK(cudaMalloc(&dF, 8192 * 64 * 2));
@@ -370,27 +341,24 @@ static void run_rate(int mode, const char* name, int grid) {
   CUtensorMap tmF;
   if (make_tmap_bhnd_16bit(&tmF, dF, 1, 1, 1, 8192, 64, 8192 * 64, 8192 * 64, 64, 128)) { printf("tmap failed\n"); return; }
   const int smem_bytes = 65536 + 65536 + 1024;
-  const bool pair = mode >= 4;
+  constexpr bool pair = kMode == 2 || kMode == 3 || kMode == 5;
   const int iters = 2000;
-  if (pair) {
-    CK(cudaFuncSetAttribute(rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid & ~1), cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = smem_bytes;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-    cfg.attrs = at, cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, rate_kernel<true>, tmF, mode, iters, dOut));
-  } else {
-    CK(cudaFuncSetAttribute(rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    rate_kernel<false><<<grid, 128, smem_bytes>>>(tmF, mode, iters, dOut);
-  }
+  if (pair && grid < 2) grid = 2;
+  CK(cudaFuncSetAttribute(rate_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pair ? (grid & ~1) : grid), cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = pair ? 2 : 1, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, rate_kernel<kMode>, tmF, fill, iters, dOut));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s: kernel failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
   long long h[3];
   CK(cudaMemcpy(h, dOut, 24, cudaMemcpyDeviceToHost));
   const double clk = (double)h[0] / (double)h[1];
-  printf("%-34s grid %3d : %7.1f clk per MMA instruction (tensor peak 64)  -> %.0f %% of peak", name, grid, clk, 6400.0 / clk);
+  printf("%-30s%s grid %3d : %6.1f clk per MMA instruction (tensor peak 64) -> %3.0f %% of peak", name, fill ? " + TMA fill" : "           ",
+         grid, clk, 6400.0 / clk);
   if (h[2]) printf("   fill %.1f B/clk", (double)h[2] / (double)h[0]);
   printf("\n");
   cudaFree(dF), cudaFree(dOut);
@@ -400,13 +368,14 @@ int main() {
   int bad = 0;
   bad += run_pair(0);
   bad += run_pair(1);
-  for (int grid : {1, 148}) {
-    run_rate(0, "1-CTA SS (A,B smem)", grid);
-    run_rate(1, "1-CTA TS (A tmem, B smem)", grid);
-    run_rate(2, "1-CTA SS + TMA fill", grid);
-    run_rate(3, "1-CTA TS + TMA fill", grid);
-    run_rate(4, "2-CTA SS (B halved)", grid == 1 ? 2 : grid);
-    run_rate(5, "2-CTA SS + TMA fill", grid == 1 ? 2 : grid);
-  }
+  for (int grid : {1, 148})
+    for (int fill : {0, 1}) {
+      run_rate<0>(fill, "1-CTA SS (A, B smem)", grid);
+      run_rate<1>(fill, "1-CTA TS (A tmem)", grid);
+      run_rate<2>(fill, "2-CTA SS (B halved)", grid);
+      run_rate<3>(fill, "2-CTA TS (B halved)", grid);
+      run_rate<4>(fill, "1-CTA TS, MN-major B (P.V)", grid);
+      run_rate<5>(fill, "2-CTA TS, MN-major B (P.V)", grid);
+    }
   return bad;
 }
