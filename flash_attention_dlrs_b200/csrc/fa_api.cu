@@ -14,6 +14,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -316,7 +317,13 @@ int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int 
   const int tpr = D / vec;
   const long long rows_per_cta = (256 / tpr) * 4;
   long long ctas = (p.total_rows + rows_per_cta - 1) / rows_per_cta;
-  if (ctas > 148 * 16) ctas = 148 * 16;  // grid-stride beyond 16 CTAs per SM
+  // grid-stride beyond kPreCtasPerSm CTAs per SM (FA_PRE_CTAS_PER_SM overrides it for measurements)
+  static const long long per_sm = [] {
+    const char* e = std::getenv("FA_PRE_CTAS_PER_SM");
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? v : 16LL;
+  }();
+  if (ctas > 148 * per_sm) ctas = 148 * per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define FA_PRE_CASE(E, T)                                                     \
   if (dtype == E && tpr == T) {                                               \
