@@ -273,11 +273,12 @@ def bare_pcie_each_way(dev, host_in, host_out, barrier):
         s1.wait_stream(cur)
         s2.wait_stream(cur)
         for hi, di, ho, do_ in zip(host_in, d_in, host_out, d_out):
-            for h in range(0, hi.shape[1], piece):
-                with torch.cuda.stream(s1):
-                    di[:, h:h + piece].copy_(hi[:, h:h + piece], non_blocking=True)
-                with torch.cuda.stream(s2):
-                    ho[:, h:h + piece].copy_(do_[:, h:h + piece], non_blocking=True)
+            for b in range(hi.shape[0]):
+                for h in range(0, hi.shape[1], piece):   # contiguous 16 MiB pieces: plain cudaMemcpyAsync, no staging
+                    with torch.cuda.stream(s1):
+                        di[b, h:h + piece].copy_(hi[b, h:h + piece], non_blocking=True)
+                    with torch.cuda.stream(s2):
+                        ho[b, h:h + piece].copy_(do_[b, h:h + piece], non_blocking=True)
         cur.wait_stream(s1)
         cur.wait_stream(s2)
 
@@ -354,6 +355,81 @@ def c4_strong(world, rank, dev, barrier):
             "n_gpus": world, "heads_per_gpu": hl, "ms_per_step": ms.item(), "tflops": fl / (ms.item() * 1e-3) / 1e12,
             "allgather_O_ms": gather_ms, "allgather_bytes_per_rank": B * hl * N * D * 2,
             "fingerprint_O_dQ_dK_dV": hashlib.sha256(fp.cpu().numpy().tobytes()).hexdigest()[:16]}
+
+
+def multi_gpu_selftest(world, rank, dev):
+    """N > 1 only: the two multi-GPU paths that are not on the timed data path, checked where the driver runs —
+    (1) head-sharded forward with O reassembled on every rank: NCCL all-gather against a per-head fingerprint of the local
+        results, and the fused gather epilogue (PeerGatherBuffer: NVLS multicast / P2P stores from the kernel) against the
+        NCCL result bit for bit;
+    (2) sequence-parallel (ring) attention, forward + backward, against the single-GPU kernels on the whole sequence
+        (NCCL transport and the NVLink peer-memory transport, causal zigzag sharding).
+    Small shapes (a few ms).  Every check ends in an all-reduce of the verdict, so the ranks stay in step."""
+    import torch.distributed as dist
+
+    from flash_attention_dlrs_b200 import _native, ring, sharding
+
+    res = {}
+
+    def agree(ok: bool) -> bool:
+        f = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
+
+    # ---- (1) gathered O
+    try:
+        B, H, N, D = 1, 2 * world, 2048, 128
+        scale = D ** -0.5
+        g = torch.Generator(device=dev).manual_seed(99)      # replicated inputs
+        Q, K, V = (torch.randn(B, H, N, D, generator=g, device=dev).to(torch.bfloat16) for _ in range(3))
+        with torch.no_grad():
+            want_full, _ = _native.forward(Q, K, V, True, scale)                      # every head on this GPU
+            got = sharding.head_sharded_attention(Q, K, V, True, scale, gather=True)  # own heads + NCCL all-gather
+        res["allgather_O_equals_single_gpu_bitwise"] = agree(torch.equal(got, want_full))
+        try:
+            buf = sharding.PeerGatherBuffer(B, H, N, D, torch.bfloat16, dev)
+            with torch.no_grad():
+                fused = sharding.head_sharded_attention(Q, K, V, True, scale, gather=buf)
+            torch.cuda.synchronize()
+            res["fused_gather_epilogue_mode"] = "multicast" if buf.multicast_base else "p2p"
+            res["fused_gather_epilogue_equals_nccl_bitwise"] = agree(torch.equal(fused, got))
+        except Exception as e:  # noqa: BLE001  (symmetric memory unavailable: the same on every rank)
+            res["fused_gather_epilogue_error"] = repr(e)[:200]
+    except Exception as e:  # noqa: BLE001
+        res["gather_error"] = repr(e)[:200]
+
+    # ---- (2) ring attention
+    try:
+        B, H, D = 1, 4, 128
+        n = 1024
+        N = n * world
+        scale = D ** -0.5
+        g = torch.Generator(device=dev).manual_seed(7)
+        Q, K, V, dO = (torch.randn(B, H, N, D, generator=g, device=dev).to(torch.bfloat16) for _ in range(4))
+        O_f, L_f = _native.forward(Q, K, V, True, scale)
+        g_f = _native.backward(Q, K, V, O_f, dO, L_f, True, scale)
+        shard = lambda t: ring.zigzag_shard(t, rank, world).contiguous()
+        q, k, v, do = (shard(t) for t in (Q, K, V, dO))
+        rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+        for name, make_tr in (("nccl", lambda: None),
+                              ("peer_memory", lambda: ring.PeerTransport(B, H, n, D, torch.bfloat16, dev, zigzag=True))):
+            try:
+                tr = make_tr()
+                O, L = ring.ring_attention_forward(q, k, v, True, scale, zigzag=True, transport=tr)
+                dQ, dK, dV = ring.ring_attention_backward(q, k, v, O, do, L, True, scale, zigzag=True, transport=tr)
+                torch.cuda.synchronize()
+                errs = {"O": (O.float() - shard(O_f).float()).abs().max().item(),
+                        "L": (L - shard(L_f.unsqueeze(-1))).abs().max().item(),
+                        "dQ": rel(dQ, shard(g_f[0])), "dK": rel(dK, shard(g_f[1])), "dV": rel(dV, shard(g_f[2]))}
+                ok = errs["O"] <= 2e-2 and errs["L"] <= 2e-3 and max(errs["dQ"], errs["dK"], errs["dV"]) <= 2e-2
+                res[f"ring_{name}_ok"] = agree(ok)
+                if rank == 0:
+                    res[f"ring_{name}_errors_vs_single_gpu"] = {a: float("%.3g" % b) for a, b in errs.items()}
+            except Exception as e:  # noqa: BLE001
+                res[f"ring_{name}_error"] = repr(e)[:200]
+    except Exception as e:  # noqa: BLE001
+        res["ring_error"] = repr(e)[:200]
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -526,6 +602,7 @@ def run_ours(args):
     del pipe
     torch.cuda.empty_cache()
     c4 = c4_strong(world, rank, dev, barrier)
+    selftest = multi_gpu_selftest(world, rank, dev) if world > 1 else None
 
     if rank == 0:
         # on rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1 on multi-rank launches; the N = 1 line carries it)
@@ -545,7 +622,7 @@ def run_ours(args):
             "roofline": roofline, "kernels": kernels,
             "kernels_note": "each kernel timed alone in its own loop (hotter than inside the mixed step: the sum of the "
                             "four can exceed ms_per_step by a few percent)",
-            "cpu_baseline": cpu, "e2e": e2e, "c4_strong": c4,
+            "cpu_baseline": cpu, "e2e": e2e, "c4_strong": c4, "multi_gpu_selftest": selftest,
             "gpu_launches": 4 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

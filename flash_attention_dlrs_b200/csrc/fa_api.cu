@@ -321,7 +321,7 @@ int fa_bwd_preprocess(const void* o, const void* dout, float* delta, int B, int 
   static const long long per_sm = [] {
     const char* e = std::getenv("FA_PRE_CTAS_PER_SM");
     const long long v = e ? std::atoll(e) : 0;
-    return v > 0 ? v : 16LL;
+    return v > 0 ? v : 32LL;
   }();
   if (ctas > 148 * per_sm) ctas = 148 * per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -178,9 +178,16 @@ class NcclTransport:
 
 class PeerTransport:
     """NVLink peer-memory transport: every rank keeps two K / V slots and two accumulator slots in torch symmetric memory
-    and PULLS what it needs from rank-1's slot with a plain device copy after a device-side barrier (about 10 us): 650 GB/s
-    per direction measured on B200 against 77 GB/s for NCCL send/recv (which, besides, needs SMs that the attention
-    CTAs occupy).  Build it once per problem shape (the rendezvous is a collective) and pass it as `transport=`."""
+    and PULLS what it needs from rank-1's slot with a plain device copy: 650 GB/s per direction measured on B200 against
+    77 GB/s for NCCL send/recv (which, besides, needs SMs that the attention CTAs occupy).  The pulls run on a SIDE
+    stream one step ahead of their use, behind a device-side barrier on a channel of their own, so that neither the
+    ~10 us barrier nor the copy sits between two steps' kernels:
+      K / V of step s+1 are pulled while step s computes (forward and backward);
+      the dK / dV sums of step s are pulled while step s's backward kernels run, and only the (memory-bound) additions
+      wait for them.
+    Build it once per problem shape (the rendezvous is a collective) and pass it as `transport=`."""
+
+    overlaps_acc = True    # ring_attention_backward may launch a step's kernels before asking for the step's sums
 
     def __init__(self, B, H, n, D, dtype, device, group=None, zigzag=False):
         import torch.distributed._symmetric_memory as symm_mem
@@ -197,23 +204,47 @@ class PeerTransport:
         self.acc_hdl = symm_mem.rendezvous(self.acc_mem, self.group)
         self.kv_prev = self.kv_hdl.get_buffer(prev, kv_shape, dtype)
         self.acc_prev = self.acc_hdl.get_buffer(prev, acc_shape, torch.float32)
+        self.side = torch.cuda.Stream(device)
+        self.ev_kv = [torch.cuda.Event() for _ in range(2)]      # slot filled (by begin or by a pull)
+        self.ev_kv_read = [torch.cuda.Event() for _ in range(2)]  # the step that computes on the slot has been enqueued
+        self.ev_acc = [torch.cuda.Event() for _ in range(2)]     # accumulator slot pulled
+        self.ev_acc_done = torch.cuda.Event()                    # this rank's additions of the last step are enqueued
 
-    def _barrier(self):
-        self.kv_hdl.barrier()
+    # channel 0: barriers on the compute stream; channel 1 / 2: the side stream's K / V and accumulator barriers
+    def _barrier(self, channel=0):
+        self.kv_hdl.barrier(channel=channel)
 
     def begin(self, K, V, chunk_shapes=None):
         self._barrier()                                       # nobody is still reading this rank's slots (previous call)
         self.kv_mem[0, 0].copy_(K), self.kv_mem[0, 1].copy_(V)
+        self.ev_kv[0].record()
         self.want_acc = chunk_shapes is not None
         return [self.kv_mem[0, 0], self.kv_mem[0, 1]]
 
     def prefetch_kv(self, s):
-        pass
+        """Called before step s's kernels are enqueued: start pulling rank-1's shard of step s (= this rank's shard of
+        step s+1) into the other slot."""
+        if s + 1 >= self.world:
+            return
+        cur, nxt = s & 1, (s + 1) & 1
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.side):
+            if s == 0:
+                self.side.wait_event(self.ev_kv[0])           # own slot 0 is filled (and every earlier kernel is done)
+            else:
+                self.side.wait_event(self.ev_kv_read[nxt])    # step s-1, which computed on slot `nxt`, is finished
+            # every rank's slot `cur` is complete (its pull of step s-1 precedes this barrier on its side stream) and
+            # nobody still pulls from this rank's slot `nxt` (rank+1 did so in its pull of step s-1)
+            self._barrier(channel=1)
+            self.kv_mem[nxt].copy_(self.kv_prev[cur])
+            self.ev_kv[nxt].record(self.side)
+        del compute
 
     def next_kv(self, s):
-        self._barrier()                                       # every rank has finished step s (kernels, sums, pulls)
-        nxt = (s + 1) & 1
-        self.kv_mem[nxt].copy_(self.kv_prev[s & 1])           # rank-1's shard of step s is this rank's shard of step s+1
+        cur, nxt = s & 1, (s + 1) & 1
+        compute = torch.cuda.current_stream()
+        self.ev_kv_read[cur].record(compute)                  # step s's kernels (enqueued above) read slot `cur`
+        compute.wait_event(self.ev_kv[nxt])
         return [self.kv_mem[nxt, 0], self.kv_mem[nxt, 1]]
 
     def _acc_list(self, slot):
@@ -222,17 +253,33 @@ class PeerTransport:
     def first_acc(self):
         return self._acc_list(0)
 
+    def prefetch_acc(self, s):
+        """Start pulling the sums that arrive at step s (rank-1's slot of step s-1); called before step s's kernels."""
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_acc_done)            # this rank's additions of step s-1 are complete ...
+            self._barrier(channel=2)                          # ... and so are everybody else's
+            self.acc_mem[s & 1].copy_(self.acc_prev[(s - 1) & 1])
+            self.ev_acc[s & 1].record(self.side)
+
     def recv_acc(self, s):
-        self.acc_mem[s & 1].copy_(self.acc_prev[(s - 1) & 1])  # after the barrier of next_kv(s - 1)
+        torch.cuda.current_stream().wait_event(self.ev_acc[s & 1])
         return self._acc_list(s & 1)
 
     def send_acc(self, s):
-        pass                                                  # the sums stay in this rank's slot; rank+1 pulls them
+        # the sums stay in this rank's slot; rank+1 pulls them once this event (and its peers') has passed the barrier
+        self.ev_acc_done.record(torch.cuda.current_stream())
 
     def final_acc(self):
-        self._barrier()
+        compute = torch.cuda.current_stream()
         home = torch.empty_like(self.acc_mem[0])
-        home.copy_(self.acc_prev[(self.world - 1) & 1])
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_acc_done)
+            self._barrier(channel=2)
+            home.copy_(self.acc_prev[(self.world - 1) & 1])
+            done = torch.cuda.Event()
+            done.record(self.side)
+        compute.wait_event(done)
+        home.record_stream(self.side)
         return [home[c, k] for c in range(self.nb) for k in range(2)]
 
 
@@ -320,24 +367,32 @@ def ring_attention_backward(Q, K, V, O, dO, L, causal: bool = False, softmax_sca
     first_q = [True] * nb
     kv = tr.begin(K, V, shapes)
     dkv_acc = tr.first_acc()                  # travelling accumulators: [chunk][dK | dV] of the visiting shard
+    overlap = bool(getattr(tr, "overlaps_acc", False))
     for s in range(G):
         c = (r - s) % G
         tr.prefetch_kv(s)
         if s > 0:
-            dkv_acc = tr.recv_acc(s)          # sums of shard c so far, arriving with it from rank r-1
-        touched = [s > 0] * nb                # at s = 0 the accumulators of the own shard start from nothing
+            if overlap:
+                tr.prefetch_acc(s)            # the arriving sums travel while this step's kernels run
+            else:
+                dkv_acc = tr.recv_acc(s)      # sums of shard c so far, arriving with it from rank r-1
+        parts = []
         for qi, (qs, q_id) in enumerate(q_blocks):
             for ki, (ks, k_id) in enumerate(_blocks(c, G, n, zigzag)):
                 rel = _relation(causal, q_id, k_id)
                 if rel is None:
                     continue
-                dq_p, dk_p, dv_p = ops.bwd(Q[:, :, qs], kv[0][:, :, ks], kv[1][:, :, ks], O[:, :, qs], dO[:, :, qs], Lb[qi],
-                                           rel, float(softmax_scale), db[qi])
-                ops.accumulate(dq_acc[qi], dq_p, first_q[qi])
-                first_q[qi] = False
-                ops.accumulate(dkv_acc[2 * ki], dk_p, not touched[ki])
-                ops.accumulate(dkv_acc[2 * ki + 1], dv_p, not touched[ki])
-                touched[ki] = True
+                parts.append((qi, ki) + tuple(ops.bwd(Q[:, :, qs], kv[0][:, :, ks], kv[1][:, :, ks], O[:, :, qs],
+                                                      dO[:, :, qs], Lb[qi], rel, float(softmax_scale), db[qi])))
+        if s > 0 and overlap:
+            dkv_acc = tr.recv_acc(s)
+        touched = [s > 0] * nb                # at s = 0 the accumulators of the own shard start from nothing
+        for qi, ki, dq_p, dk_p, dv_p in parts:   # same order of additions as the kernels were launched in: deterministic
+            ops.accumulate(dq_acc[qi], dq_p, first_q[qi])
+            first_q[qi] = False
+            ops.accumulate(dkv_acc[2 * ki], dk_p, not touched[ki])
+            ops.accumulate(dkv_acc[2 * ki + 1], dv_p, not touched[ki])
+            touched[ki] = True
         for ki in range(nb):                  # a chunk nobody on this rank attends to at s = 0 still needs defined sums
             if not touched[ki]:
                 dkv_acc[2 * ki].zero_(), dkv_acc[2 * ki + 1].zero_()
