@@ -448,7 +448,9 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int it = 0; it < n_loop; ++it) {   // (`it` counts list steps here: only stages and phases depend on it)
         const int s = it % NS, sn = (it + 1) % NS;
         const bool more = it + 1 < n_loop;
+        fa_trace(0, it, 0);
         mbar_wait(&p_full[0], it & 1);
+        fa_trace(0, it, 1);
         tc_fence_after();
         issue_grad(0, s, it == 0);
         if (more) {
@@ -456,11 +458,14 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_fence_after();
           issue_score(0, sn);
         }
+        fa_trace(0, it, 2);
         mbar_wait(&p_full[1], it & 1);
+        fa_trace(0, it, 3);
         tc_fence_after();
         issue_grad(1, s, false);
         tc_commit(&in_empty[s]);
         if (more) issue_score(1, sn);
+        fa_trace(0, it, 4);
       }
       tc_commit(&acc_full);
     }
@@ -501,8 +506,10 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // band: key j = k0 + row sees the queries i with j - win_right <= i <= j + win_left
       const int band_base = (i_begin + it) * 128 + half * 64;
       const int band_lo = k0 + row - p.win_right - band_base, band_hi = k0 + row + p.win_left - band_base;
+      if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 0);
       mbar_wait(&stat_full[s], (k / NS) & 1);
       mbar_wait(&sc_full[half], k & 1);
+      if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 1);
       tc_fence_after();
       const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
@@ -522,6 +529,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[half]);
+      if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 2);
     }
 
     // epilogue: warpgroup a stores dV, warpgroup b stores scale * dK

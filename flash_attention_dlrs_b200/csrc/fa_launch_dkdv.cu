@@ -3,6 +3,16 @@
 #include "fa_bwd_sm100.cuh"
 #include "fa_host.h"
 
+#if FA_TRACE
+// debug builds only: every translation unit has its own copy of the trace pointer (sm100_ptx.cuh)
+extern "C" int fa_debug_set_trace_dkdv(void* dev_buf, int capacity_events) {
+  long long* p = static_cast<long long*>(dev_buf);
+  cudaMemcpyToSymbol(fa::g_fa_trace, &p, sizeof(p));
+  cudaMemcpyToSymbol(fa::g_fa_trace_cap, &capacity_events, sizeof(int));
+  return 0;
+}
+#endif
+
 namespace {
 
 template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>

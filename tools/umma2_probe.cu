@@ -140,7 +140,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // The issue loop is what the attention kernels use: descriptor low words in uniform registers + compile-time offsets
 // (umma*_off), no branches — a loop with run-time branches per MMA is issue-bound (~100 clk per instruction) and says
 // nothing about the operand path.
-template <int kMode>
+template <int kMode, int kN = 128>
 __global__ void __launch_bounds__(128, 1)
 rate_kernel(const __grid_constant__ CUtensorMap tmFill, int fill, int iters, long long* out) {
   constexpr bool kPair = kMode == 2 || kMode == 3 || kMode == 5;
@@ -174,7 +174,7 @@ rate_kernel(const __grid_constant__ CUtensorMap tmFill, int fill, int iters, lon
 
   if (warp == 0 && rank == 0) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(1, kPair ? 256 : 128, 128, 0, kBmn ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_f16(1, kPair ? 256 : 128, kN, 0, kBmn ? 1 : 0);
       constexpr int kBBox = kPair ? 8192 : 16384;
       const uint32_t a_lo = umma_lo_kmajor(smem_u32(sA));
       const uint32_t b_lo = kBmn ? umma_lo_mnmajor(smem_u32(sB), 16384) : umma_lo_kmajor(smem_u32(sB));
@@ -330,7 +330,7 @@ static int run_pair(int pv) {
   return maxerr < 1e-2 ? 0 : 1;
 }
 
-template <int kMode>
+template <int kMode, int kN = 128>
 static void run_rate(int fill, const char* name, int grid) {
   uint16_t* dF;
   long long* dOut;
@@ -344,21 +344,21 @@ static void run_rate(int fill, const char* name, int grid) {
   constexpr bool pair = kMode == 2 || kMode == 3 || kMode == 5;
   const int iters = 2000;
   if (pair && grid < 2) grid = 2;
-  CK(cudaFuncSetAttribute(rate_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  CK(cudaFuncSetAttribute(rate_kernel<kMode, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pair ? (grid & ~1) : grid), cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = pair ? 2 : 1, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, rate_kernel<kMode>, tmF, fill, iters, dOut));
+  CK(cudaLaunchKernelEx(&cfg, rate_kernel<kMode, kN>, tmF, fill, iters, dOut));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s: kernel failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
   long long h[3];
   CK(cudaMemcpy(h, dOut, 24, cudaMemcpyDeviceToHost));
   const double clk = (double)h[0] / (double)h[1];
-  printf("%-30s%s grid %3d : %6.1f clk per MMA instruction (tensor peak 64) -> %3.0f %% of peak", name, fill ? " + TMA fill" : "           ",
-         grid, clk, 6400.0 / clk);
+  printf("%-30s%s grid %3d : %6.1f clk per MMA instruction (tensor peak %d) -> %3.0f %% of peak", name, fill ? " + TMA fill" : "           ",
+         grid, clk, kN / 2, 50.0 * kN / clk);
   if (h[2]) printf("   fill %.1f B/clk", (double)h[2] / (double)h[0]);
   printf("\n");
   cudaFree(dF), cudaFree(dOut);
@@ -377,5 +377,13 @@ int main() {
       run_rate<4>(fill, "1-CTA TS, MN-major B (P.V)", grid);
       run_rate<5>(fill, "2-CTA TS, MN-major B (P.V)", grid);
     }
+  // smaller N per instruction: is the single issuing thread fast enough to keep the pipe full? (the backward kernels issue
+  // their score products as N = 64 halves)
+  run_rate<0, 64>(0, "1-CTA SS N=64", 148);
+  run_rate<1, 64>(0, "1-CTA TS N=64", 148);
+  run_rate<0, 32>(0, "1-CTA SS N=32", 148);
+  run_rate<1, 32>(0, "1-CTA TS N=32", 148);
+  run_rate<2, 64>(0, "2-CTA SS N=64", 148);
+  run_rate<3, 64>(0, "2-CTA TS N=64", 148);
   return bad;
 }
