@@ -56,9 +56,11 @@ def load_peaks():
 
 def ncu_dram_bytes(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on the bench workload, from the committed
-    `ncu --set full` capture (profiles/r01_full_summary.csv, tools/gpu_prof.sh); None if the capture is absent."""
+    `ncu --set full` capture (profiles/r02_full_summary.csv, tools/r2_call14.sh); None if the capture is absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r02_full_summary.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_full_summary.csv")
     name = {"fwd": "fa_fwd_kernel", "bwd_dkdv": "fa_bwd_dkdv_kernel", "bwd_dq": "fa_bwd_dq_kernel"}.get(kernel)
     if name is None or not os.path.exists(path):
         return None

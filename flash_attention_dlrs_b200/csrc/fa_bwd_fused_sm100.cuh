@@ -116,7 +116,9 @@ __device__ __forceinline__ void st_f32x4(float* p, uint32_t a, uint32_t b, uint3
 // kept in fp32 in `pf` (dS needs it) and written back over S^T as packed 16-bit pairs.  kMask: causal diagonal block.
 // The two 32-column chunks are software-pipelined: the TMEM load of the second and the TMEM store of the first overlap
 // the exponentials (a TMEM round trip costs ~250 clk while the tensor core is busy).
-template <bool kBf16, bool kMask>
+// kPoly: which of every 8 column pairs take exp2 on the FMA pipe — the same pairs as in the two-kernel path
+// (fa_bwd_sm100.cuh), so that dK / dV stay bit-identical between the two implementations.
+template <bool kBf16, bool kMask, int kPoly>
 __device__ __forceinline__ void fused_p_chunk(uint32_t st_saddr, uint64_t sl2_2, int row, int col0, uint32_t* pf,
                                               uint32_t (&pp)[16]) {
 #pragma unroll
@@ -128,7 +130,12 @@ __device__ __forceinline__ void fused_p_chunk(uint32_t st_saddr, uint64_t sl2_2,
       const int e = g4 * 4 + u * 2;
       float x0, x1;
       f32x2_unpack(f32x2_fma(f32x2_pack_bits(pf[e], pf[e + 1]), sl2_2, nl4[u]), x0, x1);
-      float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+      float p0, p1;
+      if ((kPoly >> ((g4 * 2 + u) & 7)) & 1) {
+        ex2_poly_x2(x0, x1, p0, p1);
+      } else {
+        p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+      }
       if constexpr (kMask) {   // keep key <= query: row = key, column = query
         const int c0 = col0 + e;
         if (row > c0) p0 = 0.f;
@@ -140,17 +147,17 @@ __device__ __forceinline__ void fused_p_chunk(uint32_t st_saddr, uint64_t sl2_2,
     }
   }
 }
-template <bool kBf16, bool kMask>
+template <bool kBf16, bool kMask, int kPoly>
 __device__ __forceinline__ void fused_p_stage(uint32_t tS, uint32_t st_saddr, uint64_t sl2_2, int row, int col0,
                                               uint32_t (&pf)[64]) {
   tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&pf[0]));
   tc_wait_ld();
   tmem_ld_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&pf[32]));
   uint32_t pp[16];
-  fused_p_chunk<kBf16, kMask>(st_saddr, sl2_2, row, col0, &pf[0], pp);
+  fused_p_chunk<kBf16, kMask, kPoly>(st_saddr, sl2_2, row, col0, &pf[0], pp);
   tc_wait_ld();
   tmem_st_x16(tS, pp);
-  fused_p_chunk<kBf16, kMask>(st_saddr + 128, sl2_2, row, col0 + 32, &pf[32], pp);
+  fused_p_chunk<kBf16, kMask, kPoly>(st_saddr + 128, sl2_2, row, col0 + 32, &pf[32], pp);
   tmem_st_x16(tS + 16, pp);
 }
 
@@ -565,10 +572,11 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_after();
       // ---- P^T = exp2(S^T * scale*log2e - L[query]) : fp32 copy kept in registers for dS, 16-bit copy to TMEM
       uint32_t pf[64];
+      constexpr int kPolyMask = kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK;
       if (diag)
-        fused_p_stage<kBf16, true>(tS, st, sl2_2, row, half * 64, pf);
+        fused_p_stage<kBf16, true, kPolyMask>(tS, st, sl2_2, row, half * 64, pf);
       else
-        fused_p_stage<kBf16, false>(tS, st, sl2_2, row, half * 64, pf);
+        fused_p_stage<kBf16, false, kPolyMask>(tS, st, sl2_2, row, half * 64, pf);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_ready);

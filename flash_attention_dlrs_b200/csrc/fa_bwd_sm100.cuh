@@ -31,6 +31,11 @@
 #ifndef FA_BWD_POLY_MASK
 #define FA_BWD_POLY_MASK 0x00
 #endif
+// D = 64 halves the tensor work per exponential: there a quarter of them on the FMA pipe pays (round 2, tools/kernel_times.py
+// on config 2: dK/dV 0.676 -> 0.660 ms, dQ 0.515 -> 0.492 ms; at D = 128 the same share costs 1-4 %)
+#ifndef FA_BWD_POLY_MASK_D64
+#define FA_BWD_POLY_MASK_D64 0x88
+#endif
 
 namespace fa {
 
@@ -132,7 +137,7 @@ __device__ __forceinline__ void store_acc_rows(uint32_t taddr, int ncols, float 
 // kAmask: `mk` = this thread's 64 attention-mask bytes for the half block (non-zero = attend).
 // kBand (with kAmask): no mask bytes, the visible elements of this thread's 64 are [band_lo, band_hi].
 template <bool kBf16, bool kColStats, bool kMask, bool kTransposed, bool kStoreP, bool kDrop = false, bool kAmask = false,
-          bool kBand = false>
+          bool kBand = false, int kPoly = FA_BWD_POLY_MASK>
 __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, uint32_t st_saddr, uint64_t nl_c,
                                                      uint64_t nd_c, float sl2, int row, int col0,
                                                      uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
@@ -172,7 +177,7 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
         float x0, x1;
         f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl4[u]), x0, x1);
         float p0, p1;
-        if ((FA_BWD_POLY_MASK >> (g & 7)) & 1) {   // FMA-pipe exp2 for a share of the pairs (see fa_fwd_sm100.cuh)
+        if ((kPoly >> (g & 7)) & 1) {   // FMA-pipe exp2 for a share of the pairs (see fa_fwd_sm100.cuh)
           ex2_poly_x2(x0, x1, p0, p1);
         } else {
           p0 = ex2_approx(x0), p1 = ex2_approx(x1);
@@ -216,7 +221,7 @@ __device__ __forceinline__ void bwd_elementwise_half(uint32_t tS, uint32_t tDP, 
 // dQ kernel flavour: per-thread statistics, dS only.  The two score accumulators are copied to registers first and
 // released to the MMA warp (`sc_free`) before any arithmetic, so the next block's score MMAs overlap this stage.
 // Output: 64 values of this thread's row as 32 packed 16-bit pairs in `pd`.
-template <bool kBf16, bool kMask, bool kDrop = false, bool kAmask = false, bool kBand = false>
+template <bool kBf16, bool kMask, bool kDrop = false, bool kAmask = false, bool kBand = false, int kPoly = FA_BWD_POLY_MASK>
 __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
                                                     uint64_t nd, float sl2, int row, int col0, uint32_t (&pd)[32],
                                                     uint32_t drop_word, uint32_t drop_shift, uint32_t drop_thresh,
@@ -246,7 +251,7 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
     float x0, x1;
     f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl), x0, x1);
     float p0, p1;
-    if ((FA_BWD_POLY_MASK >> (g & 7)) & 1) {
+    if ((kPoly >> (g & 7)) & 1) {
       ex2_poly_x2(x0, x1, p0, p1);
     } else {
       p0 = ex2_approx(x0), p1 = ex2_approx(x1);
@@ -284,6 +289,8 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const BwdParams p) {
   using Cfg = BwdCfg<kD>;
   constexpr int NS = Cfg::kStages;
+  // (attention masks need exact zeros: the polynomial clamps at 2^-125, so masked variants keep MUFU)
+  constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                                   // stationary K_j
@@ -515,16 +522,16 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
       if (kAmask && band) {
         if (kCausal && it == 0)
-          bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask, kAmask>(
+          bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask, kAmask, kPolyMask>(
               tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
         else
-          bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask, kAmask>(
+          bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask, kAmask, kPolyMask>(
               tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
       } else if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
-        bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
+        bwd_elementwise_half<kBf16, true, true, true, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64, dw,
                                                                            drop_shift, p.drop.thresh, p.drop.rp, mk);
       else
-        bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64,
+        bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64,
                                                                             dw, drop_shift, p.drop.thresh, p.drop.rp, mk);
       tc_wait_st();
       tc_fence_before();
@@ -560,6 +567,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const BwdParams p) {
   using Cfg = BwdCfg<kD>;
   constexpr int NK = Cfg::kStagesK, NV = Cfg::kStagesV;
+  constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // stationary Q_i
@@ -819,23 +827,23 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t dw = drop_row + (uint32_t)(it * 64);
       if (kAmask && band) {
         if (kCausal && it == n_it - 1)
-          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
+          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
                                                                   dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
         else if (tail_mask && it == n_it - 1)
-          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
+          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
                                                                   half * 64, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mk,
                                                                   band_lo, band_hi);
         else
-          dq_elementwise_half<kBf16, false, kDrop, kAmask, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
+          dq_elementwise_half<kBf16, false, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
                                                                    dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
       } else if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
-        dq_elementwise_half<kBf16, true, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
+        dq_elementwise_half<kBf16, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
                                                         drop_shift, p.drop.thresh, p.drop.rp, mk);
       else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
-        dq_elementwise_half<kBf16, true, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
+        dq_elementwise_half<kBf16, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
                                                         half * 64, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mk);
       else
-        dq_elementwise_half<kBf16, false, kDrop, kAmask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
+        dq_elementwise_half<kBf16, false, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
                                                          drop_shift, p.drop.thresh, p.drop.rp, mk);
       if (k > 0) mbar_wait(&ds_free[half], (k - 1) & 1);          // dQ MMAs of the previous block have read the box
 #pragma unroll

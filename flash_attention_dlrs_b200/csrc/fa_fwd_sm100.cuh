@@ -28,7 +28,7 @@
 // exponentials off MUFU gives +2 %; D = 64 (half the tensor work per exponential) gains 10 % with three in eight;
 // one in two is slower everywhere (issue-slot bound).
 #ifndef FA_FWD_POLY_MASK_D128
-#define FA_FWD_POLY_MASK_D128 0x88
+#define FA_FWD_POLY_MASK_D128 0x92   // round 2 (watchdog-free build): 0.869 ms on config 3 against 0.883 (0x88), 0.909 (none), 0.966 (0xAA)
 #endif
 #ifndef FA_FWD_POLY_MASK_D64
 #define FA_FWD_POLY_MASK_D64 0x92
