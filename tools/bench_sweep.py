@@ -134,7 +134,7 @@ def cpu_torch_ms(B, H, N, D, causal, scale, mode):
     return (time.perf_counter() - t0) * 1e3 * (B * H / 2.0)
 
 
-def providers_for(dtype, causal, scale, want_ref, tutorial=None, N=0):
+def providers_for(dtype, causal, scale, want_ref, tutorial=None, N=0, deterministic_cudnn=False):
     out = {}
 
     def ours(q, k, v):
@@ -158,6 +158,13 @@ def providers_for(dtype, causal, scale, want_ref, tutorial=None, N=0):
 
         if dtype != torch.float32:
             out["torch-cudnn"] = make(SDPBackend.CUDNN_ATTENTION)
+            if deterministic_cudnn:
+                # the same backend asked for a deterministic backward (this library's backward always is)
+                def cudnn_det(q, k, v):
+                    with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+                        return torch.nn.functional.scaled_dot_product_attention(q, k, v, scale=scale, is_causal=causal)
+                cudnn_det.deterministic = True
+                out["torch-cudnn-det"] = cudnn_det
         out["torch-xformers"] = make(SDPBackend.EFFICIENT_ATTENTION)
         if N <= 4096:
             out["torch-math"] = make(SDPBackend.MATH)
@@ -185,11 +192,14 @@ def providers_for(dtype, causal, scale, want_ref, tutorial=None, N=0):
 
 
 def bench_point(B, H, N, D, dtype, causal, scale, ref, modes=("fwd", "bwd", "fwd_bwd"), reps=20, tutorial=None,
-                cpu=False):
+                cpu=False, deterministic_cudnn=False):
     g = torch.Generator(device="cpu").manual_seed(42)
     Q, K, V, dO = (torch.randn(B, H, N, D, generator=g).to(dtype).to(DEV) for _ in range(4))
     row = {}
-    for name, fn in providers_for(dtype, causal, scale, ref, tutorial, N).items():
+    for name, fn in providers_for(dtype, causal, scale, ref, tutorial, N, deterministic_cudnn).items():
+        det = getattr(fn, "deterministic", False)
+        if det:
+            torch.use_deterministic_algorithms(True, warn_only=True)
         try:
             q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
             if "fwd" in modes:
@@ -217,6 +227,9 @@ def bench_point(B, H, N, D, dtype, causal, scale, ref, modes=("fwd", "bwd", "fwd
                     del O
         except Exception as e:  # noqa
             row[f"{name}_error"] = f"{type(e).__name__}: {str(e)[-400:]}"
+        finally:
+            if det:
+                torch.use_deterministic_algorithms(False)
         torch.cuda.empty_cache()
     if cpu:
         for mode in modes:
@@ -256,7 +269,8 @@ def main():
         if (args.quick and tag == "C4") or "named" not in only:
             continue
         t0 = time.time()
-        row = bench_point(ref=ref, reps=10 if tag == "C4" else 20, tutorial=tut, cpu=not args.no_cpu and tag != "C4", **cfg)
+        row = bench_point(ref=ref, reps=10 if tag == "C4" else 20, tutorial=tut, cpu=not args.no_cpu and tag != "C4",
+                          deterministic_cudnn=True, **cfg)
         row.update(tag=tag, **{k: (str(v) if isinstance(v, torch.dtype) else v) for k, v in cfg.items()})
         results["points"].append(row)
         print(tag, {k: round(v, 3) for k, v in row.items() if isinstance(v, float)}, f"({time.time() - t0:.0f}s)", flush=True)
