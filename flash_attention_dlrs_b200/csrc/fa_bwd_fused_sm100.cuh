@@ -42,6 +42,8 @@
 #define FA_FUSED_PACE 40
 #endif
 // FA_FUSED_ABLATE 3 (timing experiment, wrong results): unordered and only half of every dQ partial leaves the SM.
+// 5 / 6 (timing experiments, order not guaranteed): turn published with a relaxed store instead of the release /
+// turns published but never waited for — which half of the hand-over costs what.
 // FA_FUSED_TURN_WARPS: 1 = the turn-taking of the ordered dQ reduction runs on two otherwise idle warps (warp 14 polls
 // the turn counter, warp 15 publishes the next turn) instead of on the reducer warps, so that neither the poll's L2 round
 // trip nor the release's wait for the drain of ~64 KiB of reductions ever blocks the warps that feed the SM -> L2 path;
@@ -444,7 +446,11 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (warp == 14) {
           // slot v & 1 of turn_ok is free once the reducer has passed visit v - 2 (it waited on it before its reductions)
           if (v >= 2) mbar_wait(&reds_out[v & 1], ((v - 2) >> 1) & 1);
+#if FA_FUSED_ABLATE == 6   // timing experiment (order NOT guaranteed): turns are published but nobody waits for them
+          if (false) {
+#else
           if (rank != 0) {
+#endif
 #if FA_WATCHDOG
             long long t0 = clock64();
 #endif
@@ -463,7 +469,11 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // every reducer thread arrived (release, CTA scope) after issuing its reductions; the gpu-scope release below
           // is cumulative over them: the next contributor's acquire of `rank + 1` orders its reductions after ours
           mbar_wait(&reds_out[v & 1], (v >> 1) & 1);
+#if FA_FUSED_ABLATE == 5   // timing experiment (order NOT guaranteed): publish the turn without the release fence
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sem), "r"(rank + 1) : "memory");
+#else
           st_release_gpu(sem, rank + 1);
+#endif
           mbar_arrive(&rel_done[v & 1]);
         }
       }
