@@ -7,9 +7,9 @@ set -e
 cd "$(dirname "$0")/.."
 CS=flash_attention_dlrs_b200/csrc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
-mkdir -p build/var/base
+mkdir -p build/var/obj/base
 for f in $CS/*.cu; do
-  o=build/var/base/$(basename $f .cu).o
+  o=build/var/obj/base/$(basename $f .cu).o
   if [ ! -f $o ] || [ -n "$(find $CS include -newer $o -type f | head -1)" ]; then
     nvcc $FLAGS -c -o $o $f &
   fi
@@ -18,15 +18,15 @@ wait
 TU=${TU:-fa_api.cu}
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
-  mkdir -p build/var/$name
+  mkdir -p build/var/obj/$name
   objs=""
   for f in $CS/*.cu; do
     b=$(basename $f .cu)
     if echo " $TU " | grep -q " $b.cu "; then
-      nvcc $FLAGS $flags -c -o build/var/$name/$b.o $f &
-      objs="$objs build/var/$name/$b.o"
+      nvcc $FLAGS $flags -c -o build/var/obj/$name/$b.o $f &
+      objs="$objs build/var/obj/$name/$b.o"
     else
-      objs="$objs build/var/base/$b.o"
+      objs="$objs build/var/obj/base/$b.o"
     fi
   done
   wait
