@@ -9,6 +9,7 @@
 #if FA_EXPERIMENTAL_FWD
 #include "fa_fwd2_sm100.cuh"
 #include "fa_fwd_w16_sm100.cuh"
+#include "fa_fwd_duo_sm100.cuh"
 #endif
 #include "fa_fwd_sm100.cuh"
 
@@ -32,6 +33,22 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     if (masked) return launch<kElt, kD, kCausal, false, true>(tq, tk, tv, p, H, B, st);
   }
 #if FA_EXPERIMENTAL_FWD
+  if constexpr (kElt < 3 && !kDrop && !kAmask) {
+    static const int duo = [] {
+      const char* e = std::getenv("FA_FWD_DUO");
+      return e ? std::atoi(e) : 0;
+    }();
+    if (duo) {
+      using CfgD = fa::FwdDuoCfg<kD>;
+      auto kernd = fa::fa_fwd_duo_kernel<kElt == 1, kD, kCausal>;
+      static std::atomic<uint64_t> smem_setd{0};
+      if (int r = fa_host::set_smem_once(kernd, CfgD::kSmemBytes, smem_setd)) return r;
+      dim3 gridd(p.q_blocks, H, B);
+      kernd<<<gridd, CfgD::kThreads, CfgD::kSmemBytes, st>>>(tq, tk, tv, p);
+      cudaError_t ed = cudaGetLastError();
+      return ed == cudaSuccess ? 0 : fa_host::cuda_fail(ed, "fa_fwd (duo) launch");
+    }
+  }
   if constexpr (kElt < 3 && !kDrop && !kAmask) {
     // experiment (slower, see above): sixteen softmax warps (fa_fwd_w16_sm100.cuh); FA_FWD_W16=0 keeps the
     // eight-warp kernel (A/B measurements, and what the feature variants still run on)

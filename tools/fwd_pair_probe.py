@@ -13,7 +13,7 @@ def t(fn, reps=20):
     for _ in range(reps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
-mode = "pair=%s,w16=%s" % (os.environ.get("FA_FWD_PAIR", "d"), os.environ.get("FA_FWD_W16", "d"))
+mode = "pair=%s,w16=%s,duo=%s" % (os.environ.get("FA_FWD_PAIR", "d"), os.environ.get("FA_FWD_W16", "d"), os.environ.get("FA_FWD_DUO", "d"))
 save = os.environ.get("FA_PROBE_SAVE")      # directory: store O / L of every shape
 cmp_ = os.environ.get("FA_PROBE_COMPARE")   # directory: compare with what another mode stored there
 small = [(2, 3, n, d, c, dt) for d in (128, 64) for n in (1, 100, 128, 200, 384, 512, 513, 640, 1024, 1100, 2048) for c in (False, True)
