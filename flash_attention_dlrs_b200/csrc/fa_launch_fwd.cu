@@ -1,8 +1,9 @@
 // fa_launch_fwd.cu — instantiations and launch dispatch of the tcgen05 forward kernel (own translation unit: see fa_host.h).
 #include "../../include/fa_b200.h"
-// FA_EXPERIMENTAL_FWD=1 also compiles two measured-and-rejected forward variants, selectable at run time with
-// FA_FWD_PAIR=1 / FA_FWD_W16=1: the CTA-pair kernel (bit-identical, 35 % slower: longer
-// hand-over chains, and shared memory was never the limit) and the sixteen-softmax-warp kernel (10 % slower).
+// FA_EXPERIMENTAL_FWD=1 also compiles three measured-and-rejected forward variants, selectable at run time with
+// FA_FWD_PAIR=1 / FA_FWD_W16=1 / FA_FWD_DUO=1: the CTA-pair kernel (bit-identical, 35 % slower:
+// longer hand-over chains, and shared memory was never the limit), the sixteen-softmax-warp kernel (10 % slower) and the
+// kernel whose two softmax warps per sub-partition share one tile (6 % slower).
 #ifndef FA_EXPERIMENTAL_FWD
 #define FA_EXPERIMENTAL_FWD 0
 #endif

@@ -324,9 +324,15 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uin
 // asm block.  If the additions are visible to the compiler it hoists all of them out of the block loop, runs out of
 // uniform registers and re-materialises every descriptor through R2UR / spills (~40 clk per MMA, measured with
 // tools/trace_dq.py), which made the single issuing thread the bottleneck of the backward kernels.
-template <uint32_t kOffA, uint32_t kOffB>
+// FA_ABLATE_SAMEDESC=1 (timing ablation, wrong results): every MMA of a group uses the group's first operand addresses,
+// so no descriptor arithmetic is left between the instructions — the upper bound of what a cheaper issue loop could give.
+#ifndef FA_ABLATE_SAMEDESC
+#define FA_ABLATE_SAMEDESC 0
+#endif
+template <uint32_t kOffA_, uint32_t kOffB_>
 __device__ __forceinline__ void umma_ss_off(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t idesc,
                                             uint32_t accumulate) {
+  constexpr uint32_t kOffA = FA_ABLATE_SAMEDESC ? 0u : kOffA_, kOffB = FA_ABLATE_SAMEDESC ? 0u : kOffB_;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -343,9 +349,10 @@ __device__ __forceinline__ void umma_ss_off(uint32_t tmem_d, uint32_t a_base, ui
       : "r"(tmem_d), "r"(a_base), "r"(b_base), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "n"(kOffA), "n"(kOffB)
       : "memory");
 }
-template <uint32_t kOffA, uint32_t kOffB>
+template <uint32_t kOffA_, uint32_t kOffB_>
 __device__ __forceinline__ void umma_ts_off(uint32_t tmem_d, uint32_t tmem_a_base, uint32_t b_base, uint32_t idesc,
                                             uint32_t accumulate) {
+  constexpr uint32_t kOffA = FA_ABLATE_SAMEDESC ? 0u : kOffA_, kOffB = FA_ABLATE_SAMEDESC ? 0u : kOffB_;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"

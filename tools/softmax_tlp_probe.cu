@@ -42,7 +42,7 @@ __device__ __forceinline__ float exp_phase(uint32_t (&sr)[kCols], uint32_t tS, f
 
 // kBg: a ninth / seventeenth warp keeps the tensor pipe saturated meanwhile (1: both operands in shared memory, like the
 // score products; 2: A from TMEM, like P.V) with accumulators in TMEM columns 256-383 — does the softmax slow down?
-template <int kCols, int kWarps, int kMask, bool kExp, int kBg>
+template <int kCols, int kWarps, int kMask, bool kExp, int kBg, int kWork = 0, int kBgN = 128, int kSame = 0>
 __global__ void __launch_bounds__(kWarps * 32 + (kBg ? 32 : 0), 1) probe(int iters, float sl2, long long* out, float* sink) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_s;
@@ -68,20 +68,22 @@ __global__ void __launch_bounds__(kWarps * 32 + (kBg ? 32 : 0), 1) probe(int ite
   if (kBg != 0 && warp == kWarps) {
     if (elect_one()) {
       uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-      constexpr uint32_t idesc = umma_idesc_f16(1, 128, 128, 0, kBg == 2 ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_f16(1, 128, kBgN, 0, kBg == 2 ? 1 : 0);
       const uint32_t a_lo = umma_lo_kmajor(smem_u32(smem));
       const uint32_t b_lo = kBg == 2 ? umma_lo_mnmajor(smem_u32(smem + 32768), 16384) : umma_lo_kmajor(smem_u32(smem + 32768));
       const uint32_t d = tmem + 256, tA = tmem + 384;
       long long n = 0;
       const long long t0 = clock64();
       for (int g = 0; !stop; ++g) {
-        if (g >= 2) mbar_wait(&bar_mma[g & 1], ((g - 2) >> 1) & 1);   // at most two groups of 8 in flight
+        // at most two groups of 8 in flight (kWork / 10 odd: no wait at all, the issue queue's back-pressure paces the thread)
+        if (((kWork / 10) & 1) == 0 && g >= 2) mbar_wait(&bar_mma[g & 1], ((g - 2) >> 1) & 1);
         static_for<0, 8>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
-          if constexpr (kBg == 2) umma_ts_off<k * 8, umma_koff_mnmajor(k)>(d, tA, b_lo, idesc, k > 0);
-          else umma_ss_off<umma_koff_kmajor(k, 16384), umma_koff_kmajor(k, 16384)>(d, a_lo, b_lo, idesc, k > 0);
+          constexpr int kk = kSame ? 0 : k;   // kSame: the same operand addresses for every instruction (no descriptor arithmetic)
+          if constexpr (kBg == 2) umma_ts_off<kk * 8, umma_koff_mnmajor(kk)>(d, tA, b_lo, idesc, k > 0);
+          else umma_ss_off<umma_koff_kmajor(kk, 16384), umma_koff_kmajor(kk, 16384)>(d, a_lo, b_lo, idesc, k > 0);
         });
-        tc_commit(&bar_mma[g & 1]);
+        if (((kWork / 10) & 1) == 0) tc_commit(&bar_mma[g & 1]);
         n += 8;
       }
       const long long t1 = clock64();
@@ -99,9 +101,36 @@ __global__ void __launch_bounds__(kWarps * 32 + (kBg ? 32 : 0), 1) probe(int ite
     for (int c = 0; c < kCols / 32; ++c) tmem_st_x32(tS + c * 32, z);
     tc_wait_st();
   }
-  __syncthreads();
+  named_bar_sync(1, kWarps * 32);   // (not __syncthreads: the background warp is already in its loop)
   float l = 0.f;
   const long long t0 = clock64();
+  if (kWork % 10 == 3 || (kWork >= 20 && (warp & 3) == 0)) {   // control: the softmax warps sleep (kWork >= 20: those of sub-partition 0 only)
+    for (int it = 0; it < iters; ++it) __nanosleep(500);
+  } else if constexpr (kWork % 10 == 2) {   // arithmetic only: no TMEM access inside the loop
+    uint32_t sr[kCols];
+#pragma unroll
+    for (int c = 0; c < kCols / 32; ++c) tmem_ld_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
+    tc_wait_ld();
+    for (int it = 0; it < iters; ++it) {
+      const uint64_t sl2_2 = f32x2_pack(sl2, sl2), nm2 = f32x2_pack(l * 1e-9f, l * 1e-9f);
+      uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t acc = 0;
+#pragma unroll
+      for (int i = 0; i < kCols / 2; ++i) {
+        const uint64_t x2 = f32x2_fma(f32x2_pack_bits(sr[2 * i], sr[2 * i + 1]), sl2_2, nm2);
+        float x0, x1, p0, p1;
+        f32x2_unpack(x2, x0, x1);
+        if ((kMask >> (i & 7)) & 1) ex2_poly_x2(x0, x1, p0, p1);
+        else p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        ls[i & 3] = f32x2_add(ls[i & 3], f32x2_pack(p0, p1));
+        acc ^= pack2<true>(p0, p1);
+      }
+      float la, lb, lc, ld;
+      f32x2_unpack(f32x2_add(ls[0], ls[1]), la, lb);
+      f32x2_unpack(f32x2_add(ls[2], ls[3]), lc, ld);
+      l += (la + lb) + (lc + ld) + __uint_as_float(acc & 0x3f803f80u);
+    }
+  } else
   for (int it = 0; it < iters; ++it) {
     uint32_t sr[kCols];
 #pragma unroll
@@ -116,7 +145,7 @@ __global__ void __launch_bounds__(kWarps * 32 + (kBg ? 32 : 0), 1) probe(int ite
       mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
     }
     const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-    if constexpr (!kExp) l += mx;
+    if constexpr (!kExp || kWork % 10 == 1) l += mx;
     else l += exp_phase<kCols, kMask>(sr, tS, sl2, -mx * sl2);
     tc_wait_st();
 #pragma unroll
@@ -136,7 +165,7 @@ __global__ void __launch_bounds__(kWarps * 32 + (kBg ? 32 : 0), 1) probe(int ite
   }
 }
 
-template <int kCols, int kWarps, int kMask, int kBg = 0>
+template <int kCols, int kWarps, int kMask, int kBg = 0, int kWork = 0, int kBgN = 128, int kSame = 0>
 static void run() {
   long long* out;
   float* sink;
@@ -149,11 +178,11 @@ static void run() {
   const int threads = kWarps * 32 + (kBg ? 32 : 0), smem = kBg ? 65536 + 1024 : 0;
   for (int e = 0; e < 2; ++e) {
     if (e) {
-      auto k = probe<kCols, kWarps, kMask, true, kBg>;
+      auto k = probe<kCols, kWarps, kMask, true, kBg, kWork, kBgN, kSame>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       k<<<148, threads, smem>>>(iters, 0.1275f, out, sink);
     } else {
-      auto k = probe<kCols, kWarps, kMask, false, kBg>;
+      auto k = probe<kCols, kWarps, kMask, false, kBg, kWork, kBgN, kSame>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       k<<<148, threads, smem>>>(iters, 0.1275f, out, sink);
     }
@@ -162,8 +191,8 @@ static void run() {
     cudaMemcpy(bg, out, 24, cudaMemcpyDeviceToHost);
     clk[e] = (double)bg[0] / iters;
   }
-  printf("bg %d: ", kBg);
-  if (kBg) printf("[tensor pipe busy beside it, %s operands: %.1f clk per MMA] ", kBg == 2 ? "TMEM A" : "shared-memory", (double)bg[1] / (double)bg[2]);
+  printf("bg %d work %d (0 all, 1 TMEM traffic only, 2 arithmetic only, 3 asleep): ", kBg, kWork);
+  if (kBg) printf("[MMA stream beside it, N = %d, %s operands%s: %.1f clk per MMA] ", kBgN, kBg == 2 ? "TMEM A" : "shared-memory", kSame ? ", same addresses" : "", (double)bg[1] / (double)bg[2]);
   const double elems = (double)kWarps * 32 * kCols;   // per round and SM
   printf("cols/warp %3d  warps %2d (%d per sub-partition)  poly mask 0x%02x : round %7.1f clk, exp phase %7.1f clk -> %6.0f clk per 128x128 tile "
          "(exp phase only %6.0f; MUFU floor %4.0f)\n", kCols, kWarps, kWarps / 4, kMask, clk[1], clk[1] - clk[0], clk[1] * 16384.0 / elems,
@@ -179,6 +208,42 @@ int main(int argc, char** argv) {
     run<128, 8, POLY_MASK, 2>();
     run<64, 8, POLY_MASK, 1>();
     run<64, 8, POLY_MASK, 2>();
+    run<128, 8, POLY_MASK, 1, 3>();
+    run<128, 8, POLY_MASK, 2, 3>();
+    run<128, 8, POLY_MASK, 1, 1>();
+    run<128, 8, POLY_MASK, 2, 1>();
+    run<128, 8, POLY_MASK, 1, 2>();
+    run<128, 8, POLY_MASK, 2, 2>();
+    run<128, 8, 0x00, 1, 2>();
+    run<128, 8, 0xff, 1, 2>();
+    run<128, 4, POLY_MASK, 1, 2>();
+    printf("-- no wait inside the issue loop\n");
+    run<128, 8, POLY_MASK, 1, 13>();
+    run<128, 8, POLY_MASK, 2, 13>();
+    run<128, 8, POLY_MASK, 1, 12>();
+    run<128, 8, POLY_MASK, 2, 12>();
+    run<128, 8, POLY_MASK, 1, 10>();
+    run<128, 8, POLY_MASK, 2, 10>();
+    printf("-- the issuing warp's sub-partition free of softmax work (no wait inside the issue loop)\n");
+    run<128, 8, POLY_MASK, 1, 32>();
+    run<128, 8, POLY_MASK, 2, 32>();
+    run<128, 8, POLY_MASK, 2, 30>();
+    printf("-- N = 64 instructions (tensor time 32 clk; shared-memory operands 48): arithmetic beside it (12), asleep (13), issuing sub-partition free (32)\n");
+    run<128, 8, POLY_MASK, 1, 13, 64>();
+    run<128, 8, POLY_MASK, 2, 13, 64>();
+    run<128, 8, POLY_MASK, 1, 12, 64>();
+    run<128, 8, POLY_MASK, 2, 12, 64>();
+    run<128, 8, POLY_MASK, 1, 32, 64>();
+    run<128, 8, POLY_MASK, 2, 32, 64>();
+    run<128, 8, POLY_MASK, 1, 12, 64, 1>();
+    run<128, 8, POLY_MASK, 2, 12, 64, 1>();
+    run<128, 8, POLY_MASK, 2, 13, 64, 1>();
+    run<128, 4, POLY_MASK, 2, 12, 64>();
+    run<128, 8, POLY_MASK, 2, 10, 64>();
+    run<128, 8, POLY_MASK, 2, 11, 64>();
+    printf("-- N = 32\n");
+    run<128, 8, POLY_MASK, 2, 13, 32>();
+    run<128, 8, POLY_MASK, 2, 12, 32>();
     return 0;
   }
   run<128, 4, POLY_MASK>();
