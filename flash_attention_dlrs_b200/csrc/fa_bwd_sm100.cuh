@@ -281,6 +281,134 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
   }
 }
 
+// ---- split elementwise stage: all eight warps work on ONE 64-column half at a time ----
+// With the two warps of a sub-partition sharing a half (32 columns each: warp w and w + 4 hold the same TMEM lanes) the
+// elementwise link of a half's chain — score MMAs -> elementwise -> gradient MMAs — gets shorter, and the other half's MMAs
+// fill the tensor pipe meanwhile.  The arithmetic per element is unchanged, so the results are bit-identical to the
+// one-warpgroup-per-half layout.  Measured (tools/kernel_times.py, profiles/r02_bwd_split.txt): D = 64, where the tensor
+// work per exponential is half and the kernels wait on the elementwise stage, gains 4-5 % (dK/dV 0.683 -> 0.657 ms, dQ
+// 0.548 -> 0.523 on config 2); D = 128 does not (dK/dV 1.68 -> 1.67, dQ 1.32 -> 1.36-1.41 ms on config 3: there a chunk of
+// 32 columns takes two warps as long, ~930 clk, as 64 columns take one warp alone, and shared-memory bandwidth — 2800 of
+// the 3340 clk of a dK/dV block — bounds the MMAs).  Hence: D = 64 only (bit k of FA_BWD_EW_SPLIT_MASK = head size 64 << k).
+#ifndef FA_BWD_EW_SPLIT_MASK
+#define FA_BWD_EW_SPLIT_MASK 0x1
+#endif
+template <int kD>
+__host__ __device__ constexpr bool bwd_ew_split() { return ((FA_BWD_EW_SPLIT_MASK >> (kD == 64 ? 0 : 1)) & 1) != 0; }
+
+// One 32-column chunk of a half (dK/dV kernel; thread = one TMEM lane).  Same arithmetic as bwd_elementwise_half.
+// tS / tDP: the chunk's 32 fp32 columns; the packed results go to the first 16 columns of the chunk's OWN score columns
+// (the partner warp's columns are never written, so the two need no synchronisation).  `cbase` = first column of the
+// chunk inside the half (0 / 32): statistics, causal / band limits, dropout words and mask bits are indexed with it.
+template <bool kBf16, bool kMask, bool kDrop, bool kAmask, bool kBand, int kPoly>
+__device__ __forceinline__ void dkdv_elementwise_chunk(uint32_t tS, uint32_t tDP, uint32_t st_saddr, float sl2, int row,
+                                                       int col0, int cbase, uint32_t drop_word, uint32_t drop_shift,
+                                                       uint32_t drop_thresh, float drop_rp, uint32_t mkw, int band_lo,
+                                                       int band_hi) {
+  uint32_t sr[32], dr[32];
+  tmem_ld_x32(tS, sr);
+  tmem_ld_x32(tDP, dr);
+  tc_wait_ld();
+  const uint64_t sl2_2 = f32x2_pack(sl2, sl2);
+  uint32_t pp[16], pd[16];
+#pragma unroll
+  for (int g4 = 0; g4 < 8; ++g4) {
+    uint64_t nl4[2], nd4[2];
+    lds_f32x2x2(st_saddr + (cbase + g4 * 4) * 4, nl4[0], nl4[1]);
+    lds_f32x2x2(st_saddr + (128 + cbase + g4 * 4) * 4, nd4[0], nd4[1]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int g = g4 * 2 + u;
+      const int e = g * 2;              // column inside the chunk
+      const int eh = cbase + e;         // column inside the half
+      float x0, x1;
+      f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl4[u]), x0, x1);
+      float p0, p1;
+      if ((kPoly >> (g & 7)) & 1) {
+        ex2_poly_x2(x0, x1, p0, p1);
+      } else {
+        p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+      }
+      if constexpr (kMask) {   // transposed scores: row = key, column = query; keep key <= query
+        const int c0 = col0 + eh;
+        if (row > c0) p0 = 0.f;
+        if (row > c0 + 1) p1 = 0.f;
+      }
+      if constexpr (kAmask && kBand) {
+        if (eh < band_lo || eh > band_hi) p0 = 0.f;
+        if (eh + 1 < band_lo || eh + 1 > band_hi) p1 = 0.f;
+      } else if constexpr (kAmask) {
+        if (!(mkw & (1u << e))) p0 = 0.f;
+        if (!(mkw & (2u << e))) p1 = 0.f;
+      }
+      float d0, d1;
+      if constexpr (kDrop) {
+        bool keep0, keep1;
+        drop_keep_pair<16>(drop_word + (uint32_t)(eh >> 1) * (1u << 15), drop_shift, drop_thresh, keep0, keep1);
+        const uint64_t f2 = f32x2_pack(keep0 ? drop_rp : 0.f, keep1 ? drop_rp : 0.f);
+        f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_fma(f32x2_pack_bits(dr[e], dr[e + 1]), f2, nd4[u])), d0, d1);
+        pp[g] = pack2<kBf16>(keep0 ? p0 : 0.f, keep1 ? p1 : 0.f);
+      } else {
+        f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd4[u])), d0, d1);
+        pp[g] = pack2<kBf16>(p0, p1);
+      }
+      pd[g] = pack2<kBf16>(d0, d1);
+    }
+  }
+  tmem_st_x16(tS, pp);
+  tmem_st_x16(tDP, pd);
+}
+
+// One 32-column chunk of a half (dQ kernel): per-thread statistics, dS only, 16 packed pairs in `pd`.
+template <bool kBf16, bool kMask, bool kDrop, bool kAmask, bool kBand, int kPoly>
+__device__ __forceinline__ void dq_elementwise_chunk(uint32_t tS, uint32_t tDP, uint64_t* sc_free_bar, uint64_t nl,
+                                                     uint64_t nd, float sl2, int row, int col0, int cbase,
+                                                     uint32_t (&pd)[16], uint32_t drop_word, uint32_t drop_shift,
+                                                     uint32_t drop_thresh, float drop_rp, uint32_t mkw, int band_lo,
+                                                     int band_hi) {
+  uint32_t sr[32], dr[32];
+  tmem_ld_x32(tS, sr);
+  tmem_ld_x32(tDP, dr);
+  tc_wait_ld();
+  tc_fence_before();
+  mbar_arrive(sc_free_bar);
+  const uint64_t sl2_2 = f32x2_pack(sl2, sl2);
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    const int e = g * 2, eh = cbase + e;
+    float x0, x1;
+    f32x2_unpack(f32x2_fma(f32x2_pack_bits(sr[e], sr[e + 1]), sl2_2, nl), x0, x1);
+    float p0, p1;
+    if ((kPoly >> (g & 7)) & 1) {
+      ex2_poly_x2(x0, x1, p0, p1);
+    } else {
+      p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+    }
+    if constexpr (kMask) {   // keep key <= `row` (row = query, column = key)
+      const int c0 = col0 + eh;
+      if (c0 > row) p0 = 0.f;
+      if (c0 + 1 > row) p1 = 0.f;
+    }
+    if constexpr (kAmask && kBand) {
+      if (eh < band_lo || eh > band_hi) p0 = 0.f;
+      if (eh + 1 < band_lo || eh + 1 > band_hi) p1 = 0.f;
+    } else if constexpr (kAmask) {
+      if (!(mkw & (1u << e))) p0 = 0.f;
+      if (!(mkw & (2u << e))) p1 = 0.f;
+    }
+    float d0, d1;
+    if constexpr (kDrop) {
+      bool keep0, keep1;
+      drop_keep_pair<8>(drop_word + (uint32_t)(eh >> 1), drop_shift, drop_thresh, keep0, keep1);
+      const uint64_t f2 = f32x2_pack(keep0 ? drop_rp : 0.f, keep1 ? drop_rp : 0.f);
+      f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_fma(f32x2_pack_bits(dr[e], dr[e + 1]), f2, nd)), d0, d1);
+    } else {
+      f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd)), d0, d1);
+    }
+    pd[g] = pack2<kBf16>(d0, d1);
+  }
+}
+
 // ================================================================================================ dK / dV
 template <bool kBf16, int kD, bool kCausal, bool kDrop = false, bool kAmask = false>
 __global__ void __launch_bounds__(384, 1)
@@ -289,6 +417,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const BwdParams p) {
   using Cfg = BwdCfg<kD>;
   constexpr int NS = Cfg::kStages;
+  constexpr bool kSplit = bwd_ew_split<kD>();
   // (attention masks need exact zeros: the polynomial clamps at 2^-125, so masked variants keep MUFU)
   constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -344,7 +473,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&sc_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], kSplit ? 256 : 128);
     }
     fence_mbar_init();
   }
@@ -435,13 +564,16 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t bq = q_mn + s * kTileLo + half * umma_koff_mnmajor(4);
         const uint32_t aP = tmem + Cfg::kTmemS + half * 64, aDS = tmem + Cfg::kTmemDP + half * 64;
         const uint32_t dV_t = tmem + Cfg::kTmemAcc0, dK_t = tmem + Cfg::kTmemAcc1;
+        // (split elementwise stage: the packed pairs of queries 32-63 of the half start at column 32, not 16)
         static_for<0, 4>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
-          umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dV_t, aP, bdo, idesc_gr, !(first && k == 0));
+          constexpr uint32_t acol = kSplit ? (k * 8 + (k >= 2 ? 16 : 0)) : k * 8;
+          umma_ts_off<acol, umma_koff_mnmajor(k)>(dV_t, aP, bdo, idesc_gr, !(first && k == 0));
         });
         static_for<0, 4>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
-          umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dK_t, aDS, bq, idesc_gr, !(first && k == 0));
+          constexpr uint32_t acol = kSplit ? (k * 8 + (k >= 2 ? 16 : 0)) : k * 8;
+          umma_ts_off<acol, umma_koff_mnmajor(k)>(dK_t, aDS, bq, idesc_gr, !(first && k == 0));
         });
       };
 
@@ -481,12 +613,69 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else {
     setmaxnreg_inc<216>();
     // ------------------------------------------------------------------ elementwise: P^T, dS^T  (warps 0-7)
-    const int half = warp >> 2;
+    const int half = warp >> 2;               // (split: epilogue role only; in the loop the warp serves both halves)
     const int row = (warp & 3) * 32 + lane;   // key row inside the block == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float sl2 = p.scale_log2;
+    if constexpr (kSplit) {
+    const int cbase = (warp >> 2) * 32;       // my 32 columns of every half
+    uint32_t drop_col = 0, drop_shift = 0;
+    if constexpr (kDrop) {
+      drop_col = drop_key(p.drop, b * p.H + h) + drop_word_index(0, k0 + row);
+      drop_shift = 8u * ((k0 + row) & 1);
+    }
+    const uint8_t* amt_row = nullptr;   // this key's row of the transposed attention mask
+    if constexpr (kAmask) {
+      if (p.amask_t)
+        amt_row = p.amask_t + (int64_t)b * p.amt_s[0] + (int64_t)h * p.amt_s[1] + (int64_t)min(k0 + row, p.N - 1) * p.amt_s[2];
+    }
+    for (int k = 0; k < n_loop; ++k) {
+      const int it = kAmask ? block_of(k) : k;
+      const int s = k % NS;
+      bool full = false;
+      if constexpr (kAmask)
+        full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)(i_begin + it) * p.ab_s[2] + jb] == 2;
+      const bool band = kAmask && !amt_row && !full;   // cut by a band mask (no mask bytes: the visible range is computed)
+      mbar_wait(&stat_full[s], (k / NS) & 1);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t mkw = 0xffffffffu;
+        if constexpr (kAmask) {
+          if (amt_row && !full) mkw = __ldg(reinterpret_cast<const uint32_t*>(amt_row + (i_begin + it) * 16 + hf * 8 + (cbase >> 3)));
+        }
+        // band: key j = k0 + row sees the queries i with j - win_right <= i <= j + win_left
+        const int band_base = (i_begin + it) * 128 + hf * 64;
+        const int band_lo = k0 + row - p.win_right - band_base, band_hi = k0 + row + p.win_left - band_base;
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), k, 3 * hf);
+        mbar_wait(&sc_full[hf], k & 1);
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), k, 3 * hf + 1);
+        tc_fence_after();
+        const uint32_t tS = tmem + Cfg::kTmemS + hf * 64 + cbase + lane_base;
+        const uint32_t tDP = tmem + Cfg::kTmemDP + hf * 64 + cbase + lane_base;
+        const uint32_t st = smem_u32(sStat + s * 256 + hf * 64);
+        const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128 + hf * 64, 0);
+        if (kAmask && band) {
+          if (kCausal && it == 0)
+            dkdv_elementwise_chunk<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, st, sl2, row, hf * 64, cbase, dw, drop_shift,
+                                                                                  p.drop.thresh, p.drop.rp, mkw, band_lo, band_hi);
+          else
+            dkdv_elementwise_chunk<kBf16, false, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, st, sl2, row, hf * 64, cbase, dw, drop_shift,
+                                                                                   p.drop.thresh, p.drop.rp, mkw, band_lo, band_hi);
+        } else if (kCausal && it == 0)   // query block == key block: the only block that needs the causal mask
+          dkdv_elementwise_chunk<kBf16, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, st, sl2, row, hf * 64, cbase, dw, drop_shift,
+                                                                               p.drop.thresh, p.drop.rp, mkw, 0, 0);
+        else
+          dkdv_elementwise_chunk<kBf16, false, kDrop, kAmask, false, kPolyMask>(tS, tDP, st, sl2, row, hf * 64, cbase, dw, drop_shift,
+                                                                                p.drop.thresh, p.drop.rp, mkw, 0, 0);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[hf]);
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), k, 3 * hf + 2);
+      }
+    }
+    } else {
     const uint32_t tS = tmem + Cfg::kTmemS + half * 64 + lane_base;
     const uint32_t tDP = tmem + Cfg::kTmemDP + half * 64 + lane_base;
-    const float sl2 = p.scale_log2;
     // dropout: this thread walks column (key) k0 + row of the mask, one hash per pair of queries (fa_dropout.cuh)
     uint32_t drop_col = 0, drop_shift = 0;
     if constexpr (kDrop) {
@@ -538,6 +727,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(&p_full[half]);
       if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 2);
     }
+    }
 
     // epilogue: warpgroup a stores dV, warpgroup b stores scale * dK
     mbar_wait(&acc_full, 0);
@@ -567,6 +757,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const BwdParams p) {
   using Cfg = BwdCfg<kD>;
   constexpr int NK = Cfg::kStagesK, NV = Cfg::kStagesV;
+  constexpr bool kSplit = bwd_ew_split<kD>();
   constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -626,8 +817,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&sc_full[t], 1);
-      mbar_init(&sc_free[t], 128);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&sc_free[t], kSplit ? 256 : 128);
+      mbar_init(&p_full[t], kSplit ? 256 : 128);
       mbar_init(&ds_free[t], 1);
     }
     fence_mbar_init();
@@ -806,6 +997,67 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_arrive(&qdo_tmem);
     }
 
+    if constexpr (kSplit) {
+    // all eight warps serve half a, then half b: warp w and w + 4 split the half's 64 key columns (32 each)
+    const int cbase = (warp >> 2) * 32;
+    uint32_t drop_row0 = 0;
+    if constexpr (kDrop) drop_row0 = drop_key(p.drop, b * p.H + h) + drop_word_index(q_row, 0);
+    for (int k = 0; k < n_loop; ++k) {
+      const int it = kAmask ? block_of(k) : k;   // key block of this step
+      bool full = false;
+      if constexpr (kAmask)
+        full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)ib * p.ab_s[2] + it] == 2;
+      const bool band = kAmask && !am_row && !full;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), it, 3 * hf);   // about to wait for scores
+        uint32_t mkw = 0xffffffffu;
+        if constexpr (kAmask) {
+          if (am_row && !full) mkw = __ldg(reinterpret_cast<const uint32_t*>(am_row + it * 16 + hf * 8 + (cbase >> 3)));
+        }
+        // band: query i = q_row sees the keys j with i - win_left <= j <= i + win_right
+        const int band_base = it * 128 + hf * 64;
+        const int band_lo = q_row - p.win_left - band_base, band_hi = q_row + p.win_right - band_base;
+        mbar_wait(&sc_full[hf], k & 1);
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), it, 3 * hf + 1);   // scores ready
+        tc_fence_after();
+        const uint32_t tSc = tmem + Cfg::kTmemS + hf * 64 + cbase + lane_base;
+        const uint32_t tDPc = tmem + Cfg::kTmemDP + hf * 64 + cbase + lane_base;
+        uint32_t pd[16];
+        const uint32_t dw = drop_row0 + (uint32_t)(it * 64 + hf * 32);
+        if (kAmask && band) {
+          if (kCausal && it == n_it - 1)
+            dq_elementwise_chunk<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd,
+                                                                               dw, drop_shift, p.drop.thresh, p.drop.rp, mkw, band_lo, band_hi);
+          else if (tail_mask && it == n_it - 1)
+            dq_elementwise_chunk<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, nv - it * 128 - 1,
+                                                                               hf * 64, cbase, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mkw,
+                                                                               band_lo, band_hi);
+          else
+            dq_elementwise_chunk<kBf16, false, kDrop, kAmask, kAmask, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd,
+                                                                                dw, drop_shift, p.drop.thresh, p.drop.rp, mkw, band_lo, band_hi);
+        } else if (kCausal && it == n_it - 1)   // key block == query block: keep key <= query
+          dq_elementwise_chunk<kBf16, true, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd, dw,
+                                                                            drop_shift, p.drop.thresh, p.drop.rp, mkw, 0, 0);
+        else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
+          dq_elementwise_chunk<kBf16, true, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, nv - it * 128 - 1,
+                                                                            hf * 64, cbase, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mkw, 0, 0);
+        else
+          dq_elementwise_chunk<kBf16, false, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd, dw,
+                                                                             drop_shift, p.drop.thresh, p.drop.rp, mkw, 0, 0);
+        if (k > 0) mbar_wait(&ds_free[hf], (k - 1) & 1);          // dQ MMAs of the previous block have read the box
+        const uint32_t sds = smem_u32(hf == 0 ? sQ : sDO);         // this half's dS box (see the MMA warp)
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, (cbase >> 3) + ch)), "r"(pd[ch * 4]),
+                       "r"(pd[ch * 4 + 1]), "r"(pd[ch * 4 + 2]), "r"(pd[ch * 4 + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[hf]);
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), it, 3 * hf + 2);   // dS handed over
+      }
+    }
+    } else {
     const uint32_t sds = smem_u32(half == 0 ? sQ : sDO);   // this half's dS box (see the MMA warp)
     for (int k = 0; k < n_loop; ++k) {
       const int it = kAmask ? block_of(k) : k;   // key block of this step
@@ -854,6 +1106,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       fence_proxy_async_smem();
       mbar_arrive(&p_full[half]);
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 2);   // dS handed over
+    }
     }
 
     // epilogue: each warpgroup stores half of the D columns of scale * dQ
