@@ -145,7 +145,7 @@ int launch_bwd32(const fa::SimtParams& p, int which, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------- backward (16-bit)
-// Workspace of the fused backward: [ticket | pad to 256 B][turn counters 2 x tiles, padded to 256 B][fp32 dQ tiles A][B]
+// Workspace of the fused backward: [ticket | pad to 256 B][turn counters 2 x tiles x chunks, padded to 256 B][fp32 dQ tiles A][B]
 struct FusedLayout {
   size_t ctrl_bytes, acc_floats, total_bytes;
   int n_blocks;
@@ -155,7 +155,7 @@ FusedLayout fused_layout(int B, int H, int N, int D, int causal) {
   FusedLayout L{};
   L.n_blocks = (N + 127) / 128;
   L.tiles = (long long)B * H * L.n_blocks;
-  L.ctrl_bytes = 256 + (((size_t)L.tiles * 2 * sizeof(int) + 255) & ~(size_t)255);
+  L.ctrl_bytes = 256 + (((size_t)L.tiles * 2 * fa::kSemPerTile * sizeof(int) + 255) & ~(size_t)255);
   L.acc_floats = (size_t)L.tiles * 128 * D;
   L.total_bytes = L.ctrl_bytes + L.acc_floats * sizeof(float) * (causal ? 1 : 2);
   return L;
@@ -172,7 +172,11 @@ int launch_bwd16_fused(const fa::BwdMaps& m, const fa::BwdParams& p, void* works
   fp.dq_acc = reinterpret_cast<float*>(ws + L.ctrl_bytes);
   fp.acc_b_off = kCausal ? 0 : (long long)L.acc_floats;
   fp.n_blocks = L.n_blocks;
+#if FA_FUSED_TMA && FA_FUSED_UNORDERED   // timing experiments: every contribution is a reduction into a zeroed workspace
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.total_bytes, st);
+#else
   cudaError_t e = cudaMemsetAsync(ws, 0, L.ctrl_bytes, st);
+#endif
   if (e != cudaSuccess) return cuda_fail(e, "fa_bwd(fused) cudaMemsetAsync");
   auto kern = fa::fa_bwd_fused_kernel<kBf16, kD, kCausal>;
   static std::atomic<uint64_t> smem_set{0};

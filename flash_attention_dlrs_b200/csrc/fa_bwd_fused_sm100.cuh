@@ -55,6 +55,21 @@
 #define FA_FUSED_HALF (FA_FUSED_ABLATE == 3 || FA_FUSED_ABLATE == 4)
 #endif
 #define FA_FUSED_UNORDERED (FA_FUSED_ABLATE == 1 || FA_FUSED_ABLATE == 2 || FA_FUSED_ABLATE == 3)
+// FA_FUSED_TMA: 1 = the dQ partial leaves the SM through the TMA engine: the reducer warps stage it in shared memory in
+// 16 KiB chunks (32 columns x 128 rows, the workspace's own [D/4][128][4] order, conflict-free 16-byte stores) and warp 15
+// issues one `cp.reduce.async.bulk ... add.f32` per chunk (a plain bulk store for the tile's first contributor); the
+// staging buffers take the place of the second dO stage, and the fixed order is kept per CHUNK (one turn counter per
+// tile and chunk, polled ahead by warp 14).  Bit-identical to the register path and to itself (tests green), but
+// measured slower (profiles/r02_fused_tma_egress.txt, config 3 causal): no egress 2.33 ms (the single dO stage alone
+// costs 0.25 ms against 2.07), unordered 4.16, ordered 6.91 — against 2.97 / 3.85 for the register path and 2.9 for the
+// two kernels.  Why no egress mechanism can win at D = 128: per visit the kernel moves 64 KiB of Q / dO in and 64 KiB of
+// fp32 partial out, and a reduction costs the L2 slices twice what a load does (21 B/clk per SM for reductions, ~42 for
+// loads, chip-wide) — 192 KiB-equivalents at ~42.6 B/clk per SM = 4600 clk per visit against 4030 of compute: the single
+// pass is bound by L2 slice throughput at ~2.35 ms (cuDNN's kernel of the same design: 2.30), whichever unit issues the
+// traffic; the TMA engine adds its in-order queue (Q / dO loads wait behind 16 KiB reductions).  Default 0.
+#ifndef FA_FUSED_TMA
+#define FA_FUSED_TMA 0
+#endif
 
 namespace fa {
 
@@ -63,9 +78,11 @@ struct FusedParams {
   float* dq_acc;         // buffer A: (B*H*n_blocks) tiles of 128 x D fp32, tile layout [D/4][128 rows][4]
   long long acc_b_off;   // floats from buffer A to buffer B (0 when causal)
   int* ticket;           // CTA ticket counter (zeroed before the launch)
-  int* sem;              // turn counters: [2][B*H*n_blocks] (zeroed before the launch)
+  int* sem;              // turn counters: [2][B*H*n_blocks][kSemPerTile] (zeroed before the launch)
   int n_blocks;
 };
+
+constexpr int kSemPerTile = 4;   // one turn counter per 32-column chunk of a tile (FA_FUSED_TMA), D <= 128
 
 template <int kD>
 struct FusedCfg {
@@ -75,7 +92,13 @@ struct FusedCfg {
   static constexpr int kDsBytes = 2 * kBoxBytes;   // dS^T: 128 key rows x 128 queries (two 64-query boxes)
   static constexpr int kStatFloats = 256;          // -lse and -delta of one query block
   static constexpr int kThreads = 512;
+  static constexpr int kChunks = kD / 32;           // dQ egress chunks of 32 columns (FA_FUSED_TMA)
+  static constexpr int kStageBytes = 128 * 32 * 4;  // one staged chunk: [8 vectors][128 rows][16 bytes]
+#if FA_FUSED_TMA
+  static constexpr int kTiles = 5 * kTileBytes + kDsBytes + 2 * kStageBytes;   // K, V, Q[2], dO, dS, staging[2]
+#else
   static constexpr int kTiles = 6 * kTileBytes + kDsBytes;   // K, V, Q[2], dO[2], dS
+#endif
   static constexpr int kCtrlBytes = 2 * kStatFloats * 4 + 256;           // statistics ring + barriers / scalars
   static constexpr int kAlignSlack = 512;   // the dynamic window starts 1024-aligned in practice (checked in-kernel)
   static constexpr int kSmemBytes = kTiles + kCtrlBytes + kAlignSlack;
@@ -205,9 +228,16 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = smem;                                   // stationary K_j
   uint8_t* sV = sK + Cfg::kTileBytes;                   // stationary V_j
   uint8_t* sQ = sV + Cfg::kTileBytes;                   // [2] streamed Q_i
+#if FA_FUSED_TMA
+  uint8_t* sDO = sQ + 2 * Cfg::kTileBytes;              // streamed dO_i (one stage)
+  uint8_t* sDS = sDO + Cfg::kTileBytes;                 // dS^T of the current visit
+  uint8_t* sStage = sDS + Cfg::kDsBytes;                // [2] staged dQ chunks
+  float* sStat = reinterpret_cast<float*>(sStage + 2 * Cfg::kStageBytes);   // [2][2][128]: -lse, -delta
+#else
   uint8_t* sDO = sQ + 2 * Cfg::kTileBytes;              // [2] streamed dO_i
   uint8_t* sDS = sDO + 2 * Cfg::kTileBytes;             // dS^T of the current visit
   float* sStat = reinterpret_cast<float*>(sDS + Cfg::kDsBytes);   // [2][2][128]: -lse, -delta
+#endif
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * Cfg::kStatFloats);
   uint64_t* kv_full = bars + 0;
   uint64_t* acc_full = bars + 1;
@@ -221,9 +251,17 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* ds_free = bars + 12;
   uint64_t* dq_full = bars + 13;
   uint64_t* dq_free = bars + 14;
+#if FA_FUSED_TMA
+  uint64_t* do_full = bars + 15;      // producer -> MMA: dO_v has landed
+  uint64_t* do_empty = bars + 16;     // MMA -> producer: dV(v), the last reader of dO_v, has completed
+  uint64_t* staged = bars + 17;       // [2] reducer -> warp 15: a chunk is in staging buffer g & 1
+  uint64_t* stage_free = bars + 19;   // [2] warp 15 -> reducer: the TMA engine has read that buffer
+  volatile int* turn_seen = reinterpret_cast<volatile int*>(bars + 21);   // warp 14 -> warp 15: chunks whose turn has come
+#else
   uint64_t* turn_ok = bars + 15;      // [2] warp 14 -> reducer: it is this CTA's turn on the tile of visit v
   uint64_t* reds_out = bars + 17;     // [2] reducer -> warps 14 / 15: the reductions of visit v have been issued
   uint64_t* rel_done = bars + 19;     // [2] warp 15 -> reducer: the turn of visit v has been passed on
+#endif
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 22);
   int* ticket_s = reinterpret_cast<int*>(bars + 23);
 
@@ -253,11 +291,21 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(ds_free, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 128);
+#if FA_FUSED_TMA
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&staged[t], 128);
+      mbar_init(&stage_free[t], 1);
+    }
+    *turn_seen = 0;
+#else
     for (int t = 0; t < 2; ++t) {
       mbar_init(&turn_ok[t], 1);
       mbar_init(&reds_out[t], 128);
       mbar_init(&rel_done[t], 1);
     }
+#endif
     fence_mbar_init();
     // Tickets are handed out in launch order: a CTA's predecessor in the dQ reduction always holds a smaller ticket.
     *ticket_s = atomicAdd(fp.ticket, 1);
@@ -313,6 +361,19 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int s = v & 1;
         const int q0 = q_block(v) * 128;
         mbar_wait(&q_empty[s], ((v >> 1) & 1) ^ 1);          // Q_{v-2}, dO_{v-2} consumed (dK(v-2) is their last reader)
+#if FA_FUSED_TMA
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&q_full[s], Cfg::kTileBytes);
+          for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+            tma_load_4d(sQ + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmQ, &q_full[s], bx * 64, q0, h, b);
+        }
+        mbar_wait(do_empty, (v & 1) ^ 1);                    // dV(v-1) has read dO_{v-1}
+        if (lane == 0) {
+          mbar_arrive_expect_tx(do_full, Cfg::kTileBytes);
+          for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+            tma_load_4d(sDO + bx * Cfg::kBoxBytes, &tmDO, do_full, bx * 64, q0, h, b);
+        }
+#else
         if (lane == 0) {
           mbar_arrive_expect_tx(&q_full[s], 2 * Cfg::kTileBytes);
           for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
@@ -320,6 +381,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tma_load_4d(sDO + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmDO, &q_full[s], bx * 64, q0, h, b);
           }
         }
+#endif
         float* st = sStat + s * Cfg::kStatFloats;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -337,6 +399,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         constexpr uint32_t idesc_dv = umma_idesc_f16(kBf16, 128, kD, 0, 1);   // [128 keys] x [D], K = 128 queries
         constexpr uint32_t idesc_dq = umma_idesc_f16(kBf16, 128, kD, 1, 1);   // [128 queries] x [D], K = 128 keys
         constexpr uint32_t kTileLo = Cfg::kTileBytes >> 4;
+        constexpr uint32_t kDoLo = FA_FUSED_TMA ? 0 : kTileLo;   // dO: one stage with the TMA egress
         const uint32_t k_lo = umma_lo_kmajor(smem_u32(sK)), v_lo = umma_lo_kmajor(smem_u32(sV));
         const uint32_t q_lo = umma_lo_kmajor(smem_u32(sQ)), do_lo = umma_lo_kmajor(smem_u32(sDO));
         const uint32_t q_mn = umma_lo_mnmajor(smem_u32(sQ), Cfg::kBoxBytes);
@@ -359,7 +422,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         };
         // dP^T = V_j dO_i^T
         auto issue_dp = [&](int s) {
-          const uint32_t bdo = do_lo + s * kTileLo;
+          const uint32_t bdo = do_lo + s * kDoLo;
           static_for<0, kD / 16>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
@@ -369,7 +432,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         };
         // dV += P^T dO_i : packed 16-bit P^T from TMEM, queries 0-63 in columns [0,32) of the S region, 64-127 in [64,96)
         auto issue_dv = [&](int s, bool first) {
-          const uint32_t bdo = do_mn + s * kTileLo;
+          const uint32_t bdo = do_mn + s * kDoLo;
           static_for<0, 8>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             umma_ts_off<(k & 3) * 8 + (k >> 2) * 64, umma_koff_mnmajor(k)>(tDV, tS, bdo, idesc_dv, !(first && k == 0));
@@ -396,6 +459,9 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         mbar_wait(kv_full, 0);
         mbar_wait(&q_full[0], 0);
+#if FA_FUSED_TMA
+        mbar_wait(do_full, 0);
+#endif
         tc_fence_after();
         issue_s(0);
         issue_dp(0);
@@ -408,6 +474,9 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (v == 0) { FA_CTA_TRACE(2); }
           tc_fence_after();
           issue_dv(s, v == 0);
+#if FA_FUSED_TMA
+          tc_commit(do_empty);
+#endif
           if (more) {
             mbar_wait(&q_full[s ^ 1], ((v + 1) >> 1) & 1);
             tc_fence_after();
@@ -425,6 +494,9 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (more) {
             mbar_wait(dq_free, v & 1);   // the reducer has copied dQ(v) out of TMEM
             fa_trace(0, v, 5);
+#if FA_FUSED_TMA
+            mbar_wait(do_full, (v + 1) & 1);
+#endif
             tc_fence_after();
             issue_dp(s ^ 1);             // Q_{v+1} / dO_{v+1} arrived before S(v+1) was issued
           }
@@ -434,7 +506,108 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     }
-#if FA_FUSED_TURN_WARPS && !FA_FUSED_UNORDERED
+#if FA_FUSED_TMA
+    else if (lane == 0) {
+      // ------------------------------------------------------------------ egress warps (14: turn poll, 15: TMA issue)
+      const int64_t tiles_bh = (int64_t)bh * n;
+      constexpr int C = Cfg::kChunks;
+      if (warp == 14) {
+#if !FA_FUSED_UNORDERED
+        // Polls the turn counters chunk by chunk, ahead of warp 15, and publishes how far the turns have come.
+        int g = 0;
+        for (int v = 0; v < n_vis; ++v) {
+          const int i = q_block(v);
+          const bool buf_b = !kCausal && i < jb;
+          const int rank = buf_b ? n - 1 - jb : v;
+          const int* sem = fp.sem + ((buf_b ? (int64_t)p.B * p.H * n : 0) + tiles_bh + i) * kSemPerTile;
+          for (int c = 0; c < C; ++c, ++g) {
+            if (rank != 0) {
+#if FA_WATCHDOG
+              long long t0 = clock64();
+#endif
+              while (ld_acquire_gpu(sem + c) != rank) {
+#if FA_WATCHDOG
+                if (clock64() - t0 > FA_WATCHDOG_CYCLES) {
+                  printf("[fa watchdog] dQ turn wait timed out: ticket %d bh %d j %d i %d chunk %d rank %d sem %d\n", ticket,
+                         bh, jb, i, c, rank, ld_acquire_gpu(sem + c));
+                  __trap();
+                }
+#endif
+              }
+            }
+            __threadfence_block();
+            *turn_seen = g + 1;
+          }
+        }
+#endif
+      } else {
+        // Issues one bulk reduction per staged chunk, hands the staging buffer back when the engine has read it, and
+        // passes the chunk's turn on when the reduction has completed.  Up to two chunks stay in flight; whenever the next
+        // chunk is not staged yet everything outstanding is completed and released first.
+        int g = 0, freed = 0, n_pend = 0;
+        int* pend_sem[3];
+        int pend_rank[3];
+        auto flush = [&](auto keep) {   // complete all but the newest `keep` groups, release their turns in order
+          constexpr int kKeep = decltype(keep)::value;
+          tma_store_wait<kKeep>();
+#if !FA_FUSED_UNORDERED
+          while (n_pend > kKeep) {
+            st_release_gpu(pend_sem[0], pend_rank[0] + 1);
+            pend_sem[0] = pend_sem[1], pend_rank[0] = pend_rank[1];
+            pend_sem[1] = pend_sem[2], pend_rank[1] = pend_rank[2];
+            --n_pend;
+          }
+#endif
+        };
+        for (int v = 0; v < (FA_FUSED_ABLATE == 2 ? 0 : n_vis); ++v) {
+          const int i = q_block(v);
+          const bool buf_b = !kCausal && i < jb;
+          const int rank = buf_b ? n - 1 - jb : v;
+          const int64_t t = (buf_b ? (int64_t)p.B * p.H * n : 0) + tiles_bh + i;
+          int* sem = fp.sem + t * kSemPerTile;
+          float* tile = fp.dq_acc + (buf_b ? fp.acc_b_off : 0) + (tiles_bh + i) * (int64_t)(128 * kD);
+          for (int c = 0; c < C; ++c, ++g) {
+            const int buf = g & 1;
+            if (!mbar_try_wait(&staged[buf], (g >> 1) & 1)) {
+              flush(std::integral_constant<int, 0>{});
+              while (freed < g) { mbar_arrive(&stage_free[freed & 1]); ++freed; }
+              mbar_wait(&staged[buf], (g >> 1) & 1);
+            }
+#if !FA_FUSED_UNORDERED
+            while (*turn_seen <= g) {}
+            __threadfence_block();
+#endif
+            asm volatile("fence.proxy.async;" ::: "memory");
+            const uint32_t src = smem_u32(sStage + buf * Cfg::kStageBytes);
+            float* dst = tile + c * (Cfg::kStageBytes / 4);
+#if FA_FUSED_UNORDERED
+            const bool plain = false;   // the host zero-fills the workspace
+#else
+            const bool plain = rank == 0;
+#endif
+            if (plain)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                           "n"(Cfg::kStageBytes)
+                           : "memory");
+            else
+              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                           "r"(src), "n"(Cfg::kStageBytes)
+                           : "memory");
+            tma_store_commit();
+#if !FA_FUSED_UNORDERED
+            pend_sem[n_pend] = sem + c, pend_rank[n_pend] = rank, ++n_pend;
+#endif
+            tma_store_wait_read<1>();     // the engine has read chunk g - 1's buffer
+            while (freed < g) { mbar_arrive(&stage_free[freed & 1]); ++freed; }
+#if !FA_FUSED_UNORDERED
+            if (n_pend == 3) flush(std::integral_constant<int, 2>{});
+#endif
+          }
+        }
+        flush(std::integral_constant<int, 0>{});
+      }
+    }
+#elif FA_FUSED_TURN_WARPS && !FA_FUSED_UNORDERED
     else if (lane == 0) {
       // ------------------------------------------------------------------ turn warps (14: acquire, 15: release)
       const int64_t tiles_bh = (int64_t)bh * n;
@@ -507,6 +680,24 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(dq_free);
       if (rt == 0) fa_trace(3, v, 2);
+#if FA_FUSED_TMA
+#if FA_FUSED_ABLATE != 2
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c) {
+        const int g = v * Cfg::kChunks + c, buf = g & 1;
+        if (g >= 2) mbar_wait(&stage_free[buf], ((g >> 1) - 1) & 1);
+        const uint32_t dst = smem_u32(sStage + buf * Cfg::kStageBytes) + row * 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + k * 2048), "r"(r[c * 32 + 4 * k]),
+                       "r"(r[c * 32 + 4 * k + 1]), "r"(r[c * 32 + 4 * k + 2]), "r"(r[c * 32 + 4 * k + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        mbar_arrive(&staged[buf]);
+      }
+#endif
+      if (rt == 0) fa_trace(3, v, 3);
+#else   // !FA_FUSED_TMA: reductions issued by the reducer threads themselves
 #if FA_FUSED_TURN_WARPS && !FA_FUSED_UNORDERED
       mbar_wait(&turn_ok[v & 1], (v >> 1) & 1);
 #elif !FA_FUSED_UNORDERED
@@ -557,6 +748,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (rt == 0) st_release_gpu(sem, rank + 1);
 #endif
       if (rt == 0) fa_trace(3, v, 3);
+#endif  // FA_FUSED_TMA
     }
   } else {
     setmaxnreg_inc<144>();
