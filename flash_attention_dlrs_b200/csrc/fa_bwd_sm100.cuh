@@ -79,16 +79,31 @@ __device__ __forceinline__ void amask_load64(uint32_t (&mk)[2], const uint8_t* s
   mk[0] = v.x, mk[1] = v.y;
 }
 
+// FA_BWD_SLOTS3: dK/dV kernel at D = 64 (with the split elementwise stage): the score halves rotate through THREE TMEM
+// slots of [S^T half 64 | dP^T half 64] columns instead of two (D = 64 leaves 128 of the 512 columns free), so the score
+// MMAs of half k + 3 are issued right after the gradient MMAs of half k and are long complete when the elementwise warps
+// get there: the chain "elementwise(k) -> gradient MMAs(k) + score MMAs(k + 2) -> elementwise(k + 2)" of the two-slot
+// pipeline is gone, the elementwise warps never wait for scores.  The Q / dO ring gets a third stage (scores run two
+// blocks ahead of the gradients).  Same arithmetic in the same order: bit-identical results.
+#ifndef FA_BWD_SLOTS3
+#define FA_BWD_SLOTS3 1
+#endif
+template <int kD>
+__host__ __device__ constexpr bool bwd_slots3();
+
 template <int kD>
 struct BwdCfg {
-  static constexpr int kStages = 2;
+  static constexpr int kStages = (kD == 64 && FA_BWD_SLOTS3) ? 3 : 2;
   static constexpr int kTileBytes = 128 * kD * 2;
   static constexpr int kBoxBytes = 128 * 128;
   static constexpr int kBoxes = kD / 64;
   static constexpr int kStatBytes = 2 * 128 * 4;  // -lse and delta of one query block
+  // dK/dV kernel: the row statistics have a ring of their own, filled by an otherwise idle warp several blocks ahead
+  // (their global loads are a dependent round trip of ~1 us; behind the Q / dO ring's release they arrived late)
+  static constexpr int kStatStages = 4;
   static constexpr int kThreads = 384;  // 8 elementwise warps + producer + MMA + 2 idle (complete the 3rd warpgroup)
   // stationary pair (2 tiles) + streamed pair ring (2 tiles per stage) + alignment slack
-  static constexpr int kSmemDkdv = 2 * kTileBytes + kStages * 2 * kTileBytes + kStages * kStatBytes + 1024;
+  static constexpr int kSmemDkdv = 2 * kTileBytes + kStages * 2 * kTileBytes + kStatStages * kStatBytes + 1024;
   // dQ kernel: Q_i/dO_i staging (2 tiles) + 3-stage K ring (K_j is held from its score MMAs until its dQ MMAs, one
   // block later) + 2-stage V ring
   static constexpr int kStagesK = 3, kStagesV = 2;
@@ -295,6 +310,8 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
 #endif
 template <int kD>
 __host__ __device__ constexpr bool bwd_ew_split() { return ((FA_BWD_EW_SPLIT_MASK >> (kD == 64 ? 0 : 1)) & 1) != 0; }
+template <int kD>
+__host__ __device__ constexpr bool bwd_slots3() { return kD == 64 && FA_BWD_SLOTS3 != 0 && bwd_ew_split<kD>(); }
 
 // One 32-column chunk of a half (dK/dV kernel; thread = one TMEM lane).  Same arithmetic as bwd_elementwise_half.
 // tS / tDP: the chunk's 32 fp32 columns; the packed results go to the first 16 columns of the chunk's OWN score columns
@@ -418,6 +435,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   using Cfg = BwdCfg<kD>;
   constexpr int NS = Cfg::kStages;
   constexpr bool kSplit = bwd_ew_split<kD>();
+  constexpr bool kSlots3 = bwd_slots3<kD>();
+  constexpr int kSlots = kSlots3 ? 3 : 2;
+  // TMEM: two slots = halves a / b at S [0,128) and dP [128,256); three slots = [S half | dP half] at 0 / 128 / 256
+  constexpr uint32_t kAccV = kSlots3 ? 384 : Cfg::kTmemAcc0, kAccK = kSlots3 ? 448 : Cfg::kTmemAcc1;
+  auto slot_s = [](int slot) -> uint32_t { return kSlots3 ? slot * 128 : Cfg::kTmemS + slot * 64; };
+  auto slot_dp = [](int slot) -> uint32_t { return kSlots3 ? slot * 128 + 64 : Cfg::kTmemDP + slot * 64; };
   // (attention masks need exact zeros: the polynomial clamps at 2^-125, so masked variants keep MUFU)
   constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -426,11 +449,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = sK + Cfg::kTileBytes;                   // stationary V_j
   uint8_t* sQ = sV + Cfg::kTileBytes;                   // [NS] streamed Q_i
   uint8_t* sDO = sQ + NS * Cfg::kTileBytes;             // [NS] streamed dO_i
-  float* sStat = reinterpret_cast<float*>(sDO + NS * Cfg::kTileBytes);  // [NS][2][128]: -lse, -delta
+  constexpr int NT = Cfg::kStatStages;
+  float* sStat = reinterpret_cast<float*>(sDO + NS * Cfg::kTileBytes);  // [NT][2][128]: -lse, -delta
 
   __shared__ uint64_t kv_full, acc_full;
-  __shared__ uint64_t in_full[NS], stat_full[NS], in_empty[NS];
-  __shared__ uint64_t sc_full[2], p_full[2];
+  __shared__ uint64_t in_full[NS], in_empty[NS], stat_full[NT], stat_empty[NT];
+  __shared__ uint64_t sc_full[kSlots], p_full[kSlots];
   __shared__ uint32_t tmem_base_s;
   // kAmask with a block summary: the query blocks with something visible for this key block, in order
   __shared__ uint16_t s_list[kAmask ? 512 : 2];
@@ -468,10 +492,13 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(&acc_full, 1);
     for (int s = 0; s < NS; ++s) {
       mbar_init(&in_full[s], 1);
-      mbar_init(&stat_full[s], 32);
       mbar_init(&in_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int s = 0; s < NT; ++s) {
+      mbar_init(&stat_full[s], 32);
+      mbar_init(&stat_empty[s], 8);   // one arrival per elementwise warp
+    }
+    for (int t = 0; t < kSlots; ++t) {
       mbar_init(&sc_full[t], 1);
       mbar_init(&p_full[t], kSplit ? 256 : 128);
     }
@@ -504,8 +531,6 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_4d(sV + bx * Cfg::kBoxBytes, &tmV, &kv_full, bx * 64, k0, h, b);
       }
     }
-    const float* lsep = p.lse + ((int64_t)b * p.H + h) * p.N;
-    const float* dlp = p.delta + ((int64_t)b * p.H + h) * p.N;
     for (int k = 0; k < n_loop; ++k) {
       const int it = kAmask ? block_of(k) : k;
       const int s = k % NS;
@@ -519,16 +544,31 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_load_4d(sDO + s * Cfg::kTileBytes + bx * Cfg::kBoxBytes, &tmDO, &in_full[s], bx * 64, q0, h, b);
         }
       }
-      float* st = sStat + s * 256;
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ row statistics of the query blocks
+    // -lse and -delta of query block k into stage k % NT, up to NT blocks ahead of the elementwise warps; all eight
+    // loads of a lane are issued before the first store (a store to shared memory through a generic pointer keeps
+    // ptxas from moving later loads above it: four dependent round trips per block instead of one)
+    const float* lsep = p.lse + ((int64_t)b * p.H + h) * p.N;
+    const float* dlp = p.delta + ((int64_t)b * p.H + h) * p.N;
+    for (int k = 0; k < n_loop; ++k) {
+      const int it = kAmask ? block_of(k) : k;
+      const int s = k % NT;
+      const int q0 = (i_begin + it) * 128;
+      float nl[4], nd[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int r = lane * 4 + e;
-        const bool ok = q0 + r < nv;
-        float nl = ok ? -lsep[q0 + r] : -INFINITY;  // rows past the valid length: P = exp2(-inf) = 0
-        if (kAmask && nl == INFINITY) nl = -INFINITY;   // a query that saw no key (L = -inf): P = 0 as well
-        st[r] = nl;
-        st[128 + r] = ok ? -dlp[q0 + r] : 0.f;
+        const int r = q0 + lane * 4 + e;
+        const bool ok = r < nv;
+        nl[e] = ok ? -__ldg(lsep + r) : -INFINITY;   // rows past the valid length: P = exp2(-inf) = 0
+        nd[e] = ok ? -__ldg(dlp + r) : 0.f;
+        if (kAmask && nl[e] == INFINITY) nl[e] = -INFINITY;   // a query that saw no key (L = -inf): P = 0 as well
       }
+      mbar_wait(&stat_empty[s], ((k / NT) & 1) ^ 1);
+      float4* st = reinterpret_cast<float4*>(sStat + s * 256);
+      st[lane] = make_float4(nl[0], nl[1], nl[2], nl[3]);
+      st[32 + lane] = make_float4(nd[0], nd[1], nd[2], nd[3]);
       mbar_arrive(&stat_full[s]);
     }
   } else if (warp == 9) {
@@ -542,10 +582,10 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t q_mn = umma_lo_mnmajor(smem_u32(sQ), Cfg::kBoxBytes);
       const uint32_t do_mn = umma_lo_mnmajor(smem_u32(sDO), Cfg::kBoxBytes);
 
-      // S^T half = K_j Q_i[half]^T ; dP^T half = V_j dO_i[half]^T
-      auto issue_score = [&](int half, int s) {
+      // S^T half = K_j Q_i[half]^T ; dP^T half = V_j dO_i[half]^T  (into TMEM slot `slot`; two slots: slot == half)
+      auto issue_score = [&](int half, int s, int slot) {
         const uint32_t bq = q_lo + s * kTileLo + half * kHalfLo, bdo = do_lo + s * kTileLo + half * kHalfLo;
-        const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
+        const uint32_t dS = tmem + slot_s(slot), dDP = tmem + slot_dp(slot);
         static_for<0, kD / 16>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
@@ -556,14 +596,14 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
           umma_ss_off<off, off>(dDP, v_lo, bdo, idesc_sc, k > 0);
         });
-        tc_commit(&sc_full[half]);
+        tc_commit(&sc_full[slot]);
       };
       // dV += P^T[half] dO_i[half] ; dK += dS^T[half] Q_i[half]
-      auto issue_grad = [&](int half, int s, bool first) {
+      auto issue_grad = [&](int half, int s, int slot, bool first) {
         const uint32_t bdo = do_mn + s * kTileLo + half * umma_koff_mnmajor(4);
         const uint32_t bq = q_mn + s * kTileLo + half * umma_koff_mnmajor(4);
-        const uint32_t aP = tmem + Cfg::kTmemS + half * 64, aDS = tmem + Cfg::kTmemDP + half * 64;
-        const uint32_t dV_t = tmem + Cfg::kTmemAcc0, dK_t = tmem + Cfg::kTmemAcc1;
+        const uint32_t aP = tmem + slot_s(slot), aDS = tmem + slot_dp(slot);
+        const uint32_t dV_t = tmem + kAccV, dK_t = tmem + kAccK;
         // (split elementwise stage: the packed pairs of queries 32-63 of the half start at column 32, not 16)
         static_for<0, 4>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
@@ -578,11 +618,48 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       };
 
       mbar_wait(&kv_full, 0);
+      if constexpr (kSlots3) {
+        // halves k = 2 * step + half rotate through slots k % 3; the scores run three halves ahead of the gradients
+        const int n_half = 2 * n_loop;
+        if (n_loop > 0) {
+          mbar_wait(&in_full[0], 0);
+          tc_fence_after();
+          issue_score(0, 0, 0);
+          issue_score(1, 0, 1);
+        }
+        if (n_loop > 1) {
+          mbar_wait(&in_full[1], 0);
+          tc_fence_after();
+          issue_score(0, 1, 2);
+        }
+        int slot = 0;
+        uint32_t ph = 0;
+        for (int k = 0; k < n_half; ++k) {
+          const int it = k >> 1, hf = k & 1, s = it % NS;
+          if (hf == 0) fa_trace(0, it, 0);
+          mbar_wait(&p_full[slot], ph);
+          fa_trace(0, it, 1 + 2 * hf);
+          tc_fence_after();
+          issue_grad(hf, s, slot, k == 0);
+          if (hf == 1) tc_commit(&in_empty[s]);
+          const int kn = k + 3;
+          if (kn < n_half) {
+            const int itn = kn >> 1, hfn = kn & 1, sn = itn % NS;
+            if (hfn == 0) {   // first touch of that block's Q / dO stage
+              mbar_wait(&in_full[sn], (itn / NS) & 1);
+              tc_fence_after();
+            }
+            issue_score(hfn, sn, slot);
+          }
+          fa_trace(0, it, 2 + 2 * hf);
+          if (++slot == 3) slot = 0, ph ^= 1;
+        }
+      } else {
       if (!kAmask || n_loop > 0) {
         mbar_wait(&in_full[0], 0);
         tc_fence_after();
-        issue_score(0, 0);
-        issue_score(1, 0);
+        issue_score(0, 0, 0);
+        issue_score(1, 0, 1);
       }
       for (int it = 0; it < n_loop; ++it) {   // (`it` counts list steps here: only stages and phases depend on it)
         const int s = it % NS, sn = (it + 1) % NS;
@@ -591,20 +668,21 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&p_full[0], it & 1);
         fa_trace(0, it, 1);
         tc_fence_after();
-        issue_grad(0, s, it == 0);
+        issue_grad(0, s, 0, it == 0);
         if (more) {
           mbar_wait(&in_full[sn], ((it + 1) / NS) & 1);
           tc_fence_after();
-          issue_score(0, sn);
+          issue_score(0, sn, 0);
         }
         fa_trace(0, it, 2);
         mbar_wait(&p_full[1], it & 1);
         fa_trace(0, it, 3);
         tc_fence_after();
-        issue_grad(1, s, false);
+        issue_grad(1, s, 1, false);
         tc_commit(&in_empty[s]);
-        if (more) issue_score(1, sn);
+        if (more) issue_score(1, sn, 1);
         fa_trace(0, it, 4);
+      }
       }
       tc_commit(&acc_full);
     }
@@ -629,6 +707,8 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (p.amask_t)
         amt_row = p.amask_t + (int64_t)b * p.amt_s[0] + (int64_t)h * p.amt_s[1] + (int64_t)min(k0 + row, p.N - 1) * p.amt_s[2];
     }
+    int slot3 = 0;          // three-slot rotation: slot and barrier phase of the current half
+    uint32_t ph3 = 0;
     for (int k = 0; k < n_loop; ++k) {
       const int it = kAmask ? block_of(k) : k;
       const int s = k % NS;
@@ -636,9 +716,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if constexpr (kAmask)
         full = use_list && p.ablock[(int64_t)b * p.ab_s[0] + (int64_t)h * p.ab_s[1] + (int64_t)(i_begin + it) * p.ab_s[2] + jb] == 2;
       const bool band = kAmask && !amt_row && !full;   // cut by a band mask (no mask bytes: the visible range is computed)
-      mbar_wait(&stat_full[s], (k / NS) & 1);
+      const int ss = k % NT;   // statistics stage
+      mbar_wait(&stat_full[ss], (k / NT) & 1);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
+        const int slot = kSlots3 ? slot3 : hf;
+        const uint32_t sc_ph = kSlots3 ? ph3 : (uint32_t)(k & 1);
         uint32_t mkw = 0xffffffffu;
         if constexpr (kAmask) {
           if (amt_row && !full) mkw = __ldg(reinterpret_cast<const uint32_t*>(amt_row + (i_begin + it) * 16 + hf * 8 + (cbase >> 3)));
@@ -647,12 +730,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int band_base = (i_begin + it) * 128 + hf * 64;
         const int band_lo = k0 + row - p.win_right - band_base, band_hi = k0 + row + p.win_left - band_base;
         if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), k, 3 * hf);
-        mbar_wait(&sc_full[hf], k & 1);
+        mbar_wait(&sc_full[slot], sc_ph);
         if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), k, 3 * hf + 1);
         tc_fence_after();
-        const uint32_t tS = tmem + Cfg::kTmemS + hf * 64 + cbase + lane_base;
-        const uint32_t tDP = tmem + Cfg::kTmemDP + hf * 64 + cbase + lane_base;
-        const uint32_t st = smem_u32(sStat + s * 256 + hf * 64);
+        const uint32_t tS = tmem + slot_s(slot) + cbase + lane_base;
+        const uint32_t tDP = tmem + slot_dp(slot) + cbase + lane_base;
+        const uint32_t st = smem_u32(sStat + ss * 256 + hf * 64);
         const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128 + hf * 64, 0);
         if (kAmask && band) {
           if (kCausal && it == 0)
@@ -669,9 +752,14 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                                                                 p.drop.thresh, p.drop.rp, mkw, 0, 0);
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[hf]);
+        mbar_arrive(&p_full[slot]);
         if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), k, 3 * hf + 2);
+        if constexpr (kSlots3) {
+          if (++slot3 == 3) slot3 = 0, ph3 ^= 1;
+        }
       }
+      __syncwarp();   // every lane has read its statistics of this block
+      if (lane == 0) mbar_arrive(&stat_empty[ss]);
     }
     } else {
     const uint32_t tS = tmem + Cfg::kTmemS + half * 64 + lane_base;
@@ -703,11 +791,12 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int band_base = (i_begin + it) * 128 + half * 64;
       const int band_lo = k0 + row - p.win_right - band_base, band_hi = k0 + row + p.win_left - band_base;
       if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 0);
-      mbar_wait(&stat_full[s], (k / NS) & 1);
+      const int ss = k % NT;   // statistics stage
+      mbar_wait(&stat_full[ss], (k / NT) & 1);
       mbar_wait(&sc_full[half], k & 1);
       if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 1);
       tc_fence_after();
-      const uint32_t st = smem_u32(sStat + s * 256 + half * 64);
+      const uint32_t st = smem_u32(sStat + ss * 256 + half * 64);
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
       if (kAmask && band) {
         if (kCausal && it == 0)
@@ -726,6 +815,8 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(&p_full[half]);
       if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 2);
+      __syncwarp();   // every lane has read its statistics of this block
+      if (lane == 0) mbar_arrive(&stat_empty[ss]);
     }
     }
 
@@ -736,11 +827,11 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool in_range = kv_row < nv;
     if (half == 0) {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dv) + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)kv_row * p.dv_s[2];
-      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc0 + lane_base, kD, kDrop ? p.drop.rp : 1.0f, dst, in_range,
+      store_acc_rows<kBf16>(tmem + kAccV + lane_base, kD, kDrop ? p.drop.rp : 1.0f, dst, in_range,
                             !kAmask || n_loop > 0);
     } else {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dk) + b * p.dk_s[0] + h * p.dk_s[1] + (int64_t)kv_row * p.dk_s[2];
-      store_acc_rows<kBf16>(tmem + Cfg::kTmemAcc1 + lane_base, kD, p.scale, dst, in_range, !kAmask || n_loop > 0);
+      store_acc_rows<kBf16>(tmem + kAccK + lane_base, kD, p.scale, dst, in_range, !kAmask || n_loop > 0);
     }
   }
 

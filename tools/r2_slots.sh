@@ -1,0 +1,11 @@
+#!/bin/bash
+# D = 64 dK/dV kernel with three TMEM slots: parity of everything that runs a D = 64 backward, then A/B timing.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -x --timeout 600 -m gpu -k "backward or bwd or grad or parity or dropout or mask or seqlens or randomized or reference" > gpurun_out/slots_pytest.log 2>&1
+echo "pytest exit=$?"; tail -3 gpurun_out/slots_pytest.log
+for i in 1 2; do
+  for v in noslots ""; do
+    if [ -n "$v" ]; then export FA_B200_LIB=$PWD/build/var/libfa_$v.so; else unset FA_B200_LIB; fi
+    timeout 120 python tools/kernel_times.py 2>&1 | grep "^lib"
+  done
+done | tee gpurun_out/slots.txt
