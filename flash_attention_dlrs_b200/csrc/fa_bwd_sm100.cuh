@@ -112,6 +112,9 @@ struct BwdCfg {
   static constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemAcc0 = 256, kTmemAcc1 = 256 + kD;
   // dQ kernel only: Q_i and dO_i as TMEM-resident A operands (packed 16-bit pairs, D/2 columns each)
   static constexpr uint32_t kTmemQA = 256 + kD, kTmemDOA = 256 + kD + kD / 2;
+  // dQ kernel at D = 64 (FA_DQ_DS_TMEM): packed dS of the current block, 32 columns per half, as the TMEM A operand of
+  // the dQ MMAs (columns [384, 448); D = 128 has no columns left and keeps dS in shared memory)
+  static constexpr uint32_t kTmemDS = 256 + 2 * kD;
 };
 
 // TMEM accumulator rows -> 16-bit global rows: thread = one row, `ncols` fp32 columns starting at taddr.
@@ -310,6 +313,14 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
 #endif
 template <int kD>
 __host__ __device__ constexpr bool bwd_ew_split() { return ((FA_BWD_EW_SPLIT_MASK >> (kD == 64 ? 0 : 1)) & 1) != 0; }
+// FA_DQ_DS_TMEM: dQ kernel at D = 64 with the split elementwise stage: dS goes back to TMEM (as in the dK/dV kernel)
+// instead of shared memory: no st.shared + fence.proxy.async in the hand-over (16 % of the elementwise warps' samples
+// in ncu), and dQ += dS K_j becomes a TS product (an SS product with N = 64 is shared-memory bound: 48 clk instead of 32).
+#ifndef FA_DQ_DS_TMEM
+#define FA_DQ_DS_TMEM 1
+#endif
+template <int kD>
+__host__ __device__ constexpr bool dq_ds_tmem() { return kD == 64 && FA_DQ_DS_TMEM != 0 && bwd_ew_split<kD>(); }
 template <int kD>
 __host__ __device__ constexpr bool bwd_slots3() { return kD == 64 && FA_BWD_SLOTS3 != 0 && bwd_ew_split<kD>(); }
 
@@ -849,6 +860,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   using Cfg = BwdCfg<kD>;
   constexpr int NK = Cfg::kStagesK, NV = Cfg::kStagesV;
   constexpr bool kSplit = bwd_ew_split<kD>();
+  constexpr bool kDsTmem = dq_ds_tmem<kD>();
   constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -988,8 +1000,12 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t dQ_t = tmem + Cfg::kTmemAcc0, aDS = ds_lo[half];
         static_for<0, 4>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
-          umma_ss_off<umma_koff_kmajor(k, Cfg::kBoxBytes), umma_koff_mnmajor(k)>(dQ_t, aDS, bk, idesc_gs,
-                                                                                !(first && k == 0));
+          if constexpr (kDsTmem)
+            umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dQ_t, tmem + Cfg::kTmemDS + half * 32, bk, idesc_gs,
+                                                     !(first && k == 0));
+          else
+            umma_ss_off<umma_koff_kmajor(k, Cfg::kBoxBytes), umma_koff_mnmajor(k)>(dQ_t, aDS, bk, idesc_gs,
+                                                                                  !(first && k == 0));
         });
         tc_commit(&ds_free[half]);
       };
@@ -1136,14 +1152,21 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         else
           dq_elementwise_chunk<kBf16, false, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd, dw,
                                                                              drop_shift, p.drop.thresh, p.drop.rp, mkw, 0, 0);
-        if (k > 0) mbar_wait(&ds_free[hf], (k - 1) & 1);          // dQ MMAs of the previous block have read the box
-        const uint32_t sds = smem_u32(hf == 0 ? sQ : sDO);         // this half's dS box (see the MMA warp)
+        if (k > 0) mbar_wait(&ds_free[hf], (k - 1) & 1);          // dQ MMAs of the previous block have read dS
+        if constexpr (kDsTmem) {
+          tc_fence_after();
+          tmem_st_x16(tmem + Cfg::kTmemDS + hf * 32 + (cbase >> 1) + lane_base, pd);
+          tc_wait_st();
+          tc_fence_before();
+        } else {
+          const uint32_t sds = smem_u32(hf == 0 ? sQ : sDO);       // this half's dS box (see the MMA warp)
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, (cbase >> 3) + ch)), "r"(pd[ch * 4]),
-                       "r"(pd[ch * 4 + 1]), "r"(pd[ch * 4 + 2]), "r"(pd[ch * 4 + 3])
-                       : "memory");
-        fence_proxy_async_smem();
+          for (int ch = 0; ch < 4; ++ch)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, (cbase >> 3) + ch)), "r"(pd[ch * 4]),
+                         "r"(pd[ch * 4 + 1]), "r"(pd[ch * 4 + 2]), "r"(pd[ch * 4 + 3])
+                         : "memory");
+          fence_proxy_async_smem();
+        }
         mbar_arrive(&p_full[hf]);
         if ((threadIdx.x & 127) == 0) fa_trace(1 + (warp >> 2), it, 3 * hf + 2);   // dS handed over
       }
