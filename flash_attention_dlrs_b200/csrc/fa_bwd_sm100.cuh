@@ -299,6 +299,88 @@ __device__ __forceinline__ void dq_elementwise_half(uint32_t tS, uint32_t tDP, u
   }
 }
 
+// ---- two-stage elementwise of the dK/dV kernel (FA_DKDV_TWO_STAGE, one warpgroup per half, no dropout; off) ----
+// The P stage needs only S^T, so it can start as soon as the S^T MMAs of the half have completed (their own commit) with
+// the dP^T MMAs running under it; the dS stage then picks dP^T up.  Same arithmetic as bwd_elementwise_half, P kept in
+// fp32 registers between the stages: bit-identical results (all GPU tests green with it).  Measured on config 3
+// (profiles/r02_dkdv_two_stage.txt): 1.70-1.72 ms against 1.66-1.68 — taking the dP^T MMAs (8 x 48 clk) off a half's
+// chain buys less than the second TMEM round trip and the lost MUFU / FMA overlap inside a thread cost.  Default 0.
+#ifndef FA_DKDV_TWO_STAGE
+#define FA_DKDV_TWO_STAGE 0
+#endif
+template <bool kBf16, bool kMask, bool kAmask, bool kBand, int kPoly>
+__device__ __forceinline__ void dkdv_p_stage(uint32_t tS, uint32_t st_saddr, float sl2, int row, int col0,
+                                             const uint32_t (&mk)[2], int band_lo, int band_hi, uint32_t (&pf)[64]) {
+  tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&pf[0]));
+  tmem_ld_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&pf[32]));
+  tc_wait_ld();
+  const uint64_t sl2_2 = f32x2_pack(sl2, sl2);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t pp[16];
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+      uint64_t nl4[2];
+      lds_f32x2x2(st_saddr + (c * 32 + g4 * 4) * 4, nl4[0], nl4[1]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g4 * 2 + u;
+        const int e = c * 32 + g * 2;
+        float x0, x1;
+        f32x2_unpack(f32x2_fma(f32x2_pack_bits(pf[e], pf[e + 1]), sl2_2, nl4[u]), x0, x1);
+        float p0, p1;
+        if ((kPoly >> (g & 7)) & 1) {
+          ex2_poly_x2(x0, x1, p0, p1);
+        } else {
+          p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        }
+        if constexpr (kMask) {   // transposed scores: row = key, column = query; keep key <= query
+          const int c0 = col0 + e;
+          if (row > c0) p0 = 0.f;
+          if (row > c0 + 1) p1 = 0.f;
+        }
+        if constexpr (kAmask && kBand) {
+          if (e < band_lo || e > band_hi) p0 = 0.f;
+          if (e + 1 < band_lo || e + 1 > band_hi) p1 = 0.f;
+        } else if constexpr (kAmask) {
+          if (!amask_byte(mk, e)) p0 = 0.f;
+          if (!amask_byte(mk, e + 1)) p1 = 0.f;
+        }
+        pf[e] = __float_as_uint(p0);
+        pf[e + 1] = __float_as_uint(p1);
+        pp[g] = pack2<kBf16>(p0, p1);
+      }
+    }
+    tmem_st_x16(tS + c * 16, pp);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ void dkdv_ds_stage(uint32_t tDP, uint32_t st_saddr, const uint32_t (&pf)[64]) {
+  uint32_t dr[64];
+  tmem_ld_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
+  tmem_ld_x32(tDP + 32, *reinterpret_cast<uint32_t(*)[32]>(&dr[32]));
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t pd[16];
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+      uint64_t nd4[2];
+      lds_f32x2x2(st_saddr + (128 + c * 32 + g4 * 4) * 4, nd4[0], nd4[1]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g4 * 2 + u;
+        const int e = c * 32 + g * 2;
+        float d0, d1;
+        f32x2_unpack(f32x2_mul(f32x2_pack_bits(pf[e], pf[e + 1]), f32x2_add(f32x2_pack_bits(dr[e], dr[e + 1]), nd4[u])),
+                     d0, d1);
+        pd[g] = pack2<kBf16>(d0, d1);
+      }
+    }
+    tmem_st_x16(tDP + c * 16, pd);
+  }
+}
+
 // ---- split elementwise stage: all eight warps work on ONE 64-column half at a time ----
 // With the two warps of a sub-partition sharing a half (32 columns each: warp w and w + 4 hold the same TMEM lanes) the
 // elementwise link of a half's chain — score MMAs -> elementwise -> gradient MMAs — gets shorter, and the other half's MMAs
@@ -448,6 +530,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr bool kSplit = bwd_ew_split<kD>();
   constexpr bool kSlots3 = bwd_slots3<kD>();
   constexpr int kSlots = kSlots3 ? 3 : 2;
+  constexpr bool kTwoStage = FA_DKDV_TWO_STAGE != 0 && !kSplit && !kDrop;
   // TMEM: two slots = halves a / b at S [0,128) and dP [128,256); three slots = [S half | dP half] at 0 / 128 / 256
   constexpr uint32_t kAccV = kSlots3 ? 384 : Cfg::kTmemAcc0, kAccK = kSlots3 ? 448 : Cfg::kTmemAcc1;
   auto slot_s = [](int slot) -> uint32_t { return kSlots3 ? slot * 128 : Cfg::kTmemS + slot * 64; };
@@ -466,6 +549,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ uint64_t kv_full, acc_full;
   __shared__ uint64_t in_full[NS], in_empty[NS], stat_full[NT], stat_empty[NT];
   __shared__ uint64_t sc_full[kSlots], p_full[kSlots];
+  __shared__ uint64_t s_full[2];   // two-stage elementwise: the S^T MMAs of a half have completed
   __shared__ uint32_t tmem_base_s;
   // kAmask with a block summary: the query blocks with something visible for this key block, in order
   __shared__ uint16_t s_list[kAmask ? 512 : 2];
@@ -513,6 +597,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&sc_full[t], 1);
       mbar_init(&p_full[t], kSplit ? 256 : 128);
     }
+    for (int t = 0; t < 2; ++t) mbar_init(&s_full[t], 1);
     fence_mbar_init();
   }
   if (warp == 8 && lane == 0) {
@@ -602,6 +687,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
           umma_ss_off<off, off>(dS, k_lo, bq, idesc_sc, k > 0);
         });
+        if constexpr (kTwoStage) tc_commit(&s_full[slot]);
         static_for<0, kD / 16>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
@@ -804,10 +890,29 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 0);
       const int ss = k % NT;   // statistics stage
       mbar_wait(&stat_full[ss], (k / NT) & 1);
+      const uint32_t st = smem_u32(sStat + ss * 256 + half * 64);
+      if constexpr (kTwoStage) {
+        mbar_wait(&s_full[half], k & 1);
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 1);
+        tc_fence_after();
+        uint32_t pf[64];
+        const bool diag = kCausal && it == 0;   // query block == key block: the only block that needs the causal mask
+        if (kAmask && band) {
+          if (diag) dkdv_p_stage<kBf16, true, kAmask, kAmask, kPolyMask>(tS, st, sl2, row, half * 64, mk, band_lo, band_hi, pf);
+          else dkdv_p_stage<kBf16, false, kAmask, kAmask, kPolyMask>(tS, st, sl2, row, half * 64, mk, band_lo, band_hi, pf);
+        } else if (diag) {
+          dkdv_p_stage<kBf16, true, kAmask, false, kPolyMask>(tS, st, sl2, row, half * 64, mk, 0, 0, pf);
+        } else {
+          dkdv_p_stage<kBf16, false, kAmask, false, kPolyMask>(tS, st, sl2, row, half * 64, mk, 0, 0, pf);
+        }
+        mbar_wait(&sc_full[half], k & 1);
+        if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 3);
+        tc_fence_after();
+        dkdv_ds_stage<kBf16>(tDP, st, pf);
+      } else {
       mbar_wait(&sc_full[half], k & 1);
       if ((threadIdx.x & 127) == 0) fa_trace(1 + half, k, 1);
       tc_fence_after();
-      const uint32_t st = smem_u32(sStat + ss * 256 + half * 64);
       const uint32_t dw = drop_col + drop_word_index((i_begin + it) * 128, 0);
       if (kAmask && band) {
         if (kCausal && it == 0)
@@ -822,6 +927,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       else
         bwd_elementwise_half<kBf16, true, false, true, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, st, 0ull, 0ull, sl2, row, half * 64,
                                                                             dw, drop_shift, p.drop.thresh, p.drop.rp, mk);
+      }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[half]);

@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -x --timeout 600 -m gpu -k "backward or bwd or grad or parity or dropout or mask or seqlens or randomized or reference" > gpurun_out/dstmem_pytest.log 2>&1
-echo "pytest exit=$?"; tail -3 gpurun_out/dstmem_pytest.log
+timeout 900 python -m pytest tests -q -x --timeout 600 -m gpu -k "backward or bwd or grad or parity or dropout or mask or seqlens or randomized or reference" > gpurun_out/twostage_pytest.log 2>&1
+echo "pytest exit=$?"; tail -3 gpurun_out/twostage_pytest.log
 for i in 1 2; do
-  for v in ""; do
+  for v in onestage ""; do
     if [ -n "$v" ]; then export FA_B200_LIB=$PWD/build/var/libfa_$v.so; else unset FA_B200_LIB; fi
     timeout 120 python tools/kernel_times.py 2>&1 | grep "^lib"
   done
-done | tee gpurun_out/dstmem.txt
+done | tee gpurun_out/twostage.txt
