@@ -108,6 +108,54 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
     return LIB_PATH
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# C++ autograd node over the C ABI (csrc/torch_binding.cpp): the plain FlashAttention.apply(Q, K, V[, causal, scale])
+# without the interpreter on the launch path.  Host plumbing only — it calls the same entry points of libfa_b200.so.
+TORCH_BINDING_SRC = CSRC / "torch_binding.cpp"
+
+
+def torch_binding_path() -> Path:
+    import sysconfig
+    return PKG_DIR / ("_fa_torch" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def torch_binding_needs_build() -> bool:
+    out = torch_binding_path()
+    if not out.exists():
+        return True
+    t = out.stat().st_mtime
+    return TORCH_BINDING_SRC.stat().st_mtime > t or HEADER.stat().st_mtime > t
+
+
+def build_torch_binding(force: bool = False) -> Path:
+    """g++ csrc/torch_binding.cpp -> _fa_torch<EXT_SUFFIX> next to libfa_b200.so (which it links by $ORIGIN)."""
+    out = torch_binding_path()
+    if not force and not torch_binding_needs_build():
+        return out
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension
+    cxx = shutil.which("g++") or "g++"
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_fa_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           "-I", str(REPO_ROOT / "include"), "-I", sysconfig.get_paths()["include"], "-I", cuda_inc]
+    for inc in cpp_extension.include_paths():
+        cmd += ["-isystem", inc]
+    tmp = out.with_suffix(".tmp%d" % os.getpid())
+    cmd += [str(TORCH_BINDING_SRC), "-o", str(tmp), "-L", str(PKG_DIR), "-l:libfa_b200.so", "-Wl,-rpath,$ORIGIN"]
+    for lp in cpp_extension.library_paths():
+        cmd += ["-L", lp]
+    cmd += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        if tmp.exists():
+            tmp.unlink()
+        raise FlashAttentionLibraryError("building the torch binding failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, out)
+    return out
+
+
 _lock = threading.Lock()
 _lib = None
 

@@ -18,11 +18,36 @@ Differences from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _native
 
 MIN_TENSOR_SIZE = 16  # flash_attention_torch.py:5
+
+# The plain call FlashAttention.apply(Q, K, V[, causal, softmax_scale]) — the only one the reference has — is served by a
+# C++ autograd node over the same C-ABI entry points when the in-tree extension is built (csrc/torch_binding.cpp): no
+# interpreter, ctypes marshalling or GIL hand-over on the launch path, which is what bounds a step below N ~ 1024.
+# Everything else (seqlens, dropout, masks, padded head sizes, FP8, errors) runs the Python Function below.  Both call the
+# same kernels with the same arguments: results are bit-identical (tests/test_gpu_parity.py).  Not used with FA_B200_LIB
+# (an alternative build of the library) or FA_B200_NO_CPP_NODE=1.
+USE_CPP_NODE = True
+_cpp_node_cache = []
+
+
+def _cpp_node():
+    if not _cpp_node_cache:
+        node = None
+        if not os.environ.get("FA_B200_LIB") and os.environ.get("FA_B200_NO_CPP_NODE") != "1":
+            try:
+                from . import _lib
+                _lib.load()   # the library first: a missing libfa_b200.so must fail with the loader's message
+                from . import _fa_torch as node
+            except ImportError:
+                node = None
+        _cpp_node_cache.append(node)
+    return _cpp_node_cache[0]
 
 
 def convert_triton_dtype(torch_dtype):
@@ -42,6 +67,16 @@ def _validate(Q, K, V):
 
 
 class FlashAttention(torch.autograd.Function):
+    @classmethod
+    def apply(cls, Q, K, V, causal=False, softmax_scale=1.0, seqlens=None, dropout_p=0.0, dropout_seed=None,
+              attn_mask=None):
+        if USE_CPP_NODE and seqlens is None and attn_mask is None and not dropout_p:
+            node = _cpp_node()
+            if (node is not None and isinstance(Q, torch.Tensor) and isinstance(K, torch.Tensor)
+                    and isinstance(V, torch.Tensor) and node.supported(Q, K, V)):
+                return node.flash_attention(Q, K, V, bool(causal), float(softmax_scale))
+        return super().apply(Q, K, V, causal, softmax_scale, seqlens, dropout_p, dropout_seed, attn_mask)
+
     @staticmethod
     def forward(ctx, Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, causal: bool = False,
                 softmax_scale: float = 1.0, seqlens=None, dropout_p: float = 0.0, dropout_seed=None,

@@ -35,4 +35,6 @@ def _built_library():
 
     if not _lib.LIB_PATH.exists():
         _lib.build()
+    if not os.environ.get("FA_B200_LIB"):
+        _lib.build_torch_binding()   # the C++ autograd node over the C ABI (no-op when up to date)
     return _lib.LIB_PATH

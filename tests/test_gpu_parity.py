@@ -254,6 +254,37 @@ def test_autograd_function_matches_functional_pair():
     assert torch.equal(O3, O4)
 
 
+@pytest.mark.parametrize("dtype,D,N", [(torch.bfloat16, 128, 512), (torch.float16, 64, 333), (torch.float32, 32, 200),
+                                       (torch.bfloat16, 64, 1)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_cpp_autograd_node_is_bitwise_the_python_function(dtype, D, N, causal, monkeypatch):
+    """FlashAttention.apply's plain form runs the C++ autograd node (csrc/torch_binding.cpp); forcing the Python Function
+    must give the same bits, for contiguous inputs and for strided views (a head slice, a transposed layout)."""
+    from flash_attention_dlrs_b200 import flash_attention_torch as fat
+    node = fat._cpp_node()
+    assert node is not None, "the torch binding is not built"
+    base = [t.to(DEV) for t in make_inputs(21, 2, 5, N, D, dtype)]
+    views = [[t[:, 1:4] for t in base],                                            # head slice: strided, kernel-legal
+             [t.transpose(1, 2).contiguous().transpose(1, 2) for t in base]]       # (B, N, H, D) memory layout
+    for Q, K, V, dO in views:
+        assert node.supported(Q, K, V)
+        outs = []
+        for use_cpp in (True, False):
+            monkeypatch.setattr(fat, "USE_CPP_NODE", use_cpp)
+            q, k, v = (t.detach().clone().requires_grad_(True) if False else t.detach().requires_grad_(True) for t in (Q, K, V))
+            O = FlashAttention.apply(q, k, v, causal, 0.11)
+            assert (type(O.grad_fn).__name__ == "FlashAttentionBackward") != use_cpp   # which node recorded the graph
+            O.backward(dO)
+            outs.append((O.detach(), q.grad, k.grad, v.grad))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+    # no graph under no_grad, and unsupported forms fall through to the Python Function (padded head size)
+    with torch.no_grad():
+        assert FlashAttention.apply(*views[0][:3], causal, 0.11).grad_fn is None
+    Qp = torch.randn(1, 2, 64, 40, device=DEV, dtype=torch.bfloat16)
+    assert not node.supported(Qp, Qp, Qp) and FlashAttention.apply(Qp, Qp, Qp).shape == Qp.shape
+
+
 def test_preprocess_parity():
     for dtype, D in ((torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)):
         O, dO = (torch.randn(2, 5, 300, D, device=DEV).to(dtype) for _ in range(2))

@@ -48,8 +48,8 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     causal = lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1, 1, 4)
     full = lib.fa_bwd_workspace_bytes(2, 32, 8192, 128, 1, 0, 4)
     tiles = 2 * 32 * 64
-    assert causal == 256 + tiles * 8 + tiles * 128 * 128 * 4
-    assert full == 256 + tiles * 8 + 2 * tiles * 128 * 128 * 4
+    assert causal == 256 + tiles * 32 + tiles * 128 * 128 * 4   # ticket | 2 x 4 turn counters per tile | fp32 tiles
+    assert full == 256 + tiles * 32 + 2 * tiles * 128 * 128 * 4
     with pytest.raises(_lib.FlashAttentionLibraryError):
         _lib.check(-1, "fa_fwd")
 
@@ -294,3 +294,16 @@ def test_attention_mask_packing_on_cpu():
     full = _native.AttentionMask(torch.ones(256, 256, dtype=torch.bool).tril())
     assert full.blocks.flatten().tolist() == [1, 0, 2, 1]   # diagonal blocks mixed, lower block fully visible, upper empty
     assert _native.AttentionMask(torch.ones(N, N)).blocks[0, 0].tolist() == [[2, 2, 1], [2, 2, 1], [1, 1, 1]]   # ragged edge
+
+
+def test_cpp_autograd_node_loads_and_declines_what_it_does_not_serve():
+    """csrc/torch_binding.cpp: the in-tree extension imports, binds the same ABI version as the ctypes handle, and refuses
+    (-> Python Function, which owns the errors) everything but plain same-shape CUDA tensors at kernel head sizes."""
+    node = fat._cpp_node()
+    assert node is not None, "flash_attention_dlrs_b200/_fa_torch*.so is not built (python -c 'import __graft_entry__ as g; g.build()')"
+    assert node.abi_version() == _lib.load().fa_version()
+    q = torch.randn(1, 2, 128, 64)
+    assert not node.supported(q, q, q)                      # CPU tensors
+    with pytest.raises(NotImplementedError):
+        fat.FlashAttention.apply(q, q, q)                   # ... raise like the reference, through the Python Function
+    assert fat.FlashAttentionDeterministic.apply.__func__ is fat.FlashAttention.apply.__func__
