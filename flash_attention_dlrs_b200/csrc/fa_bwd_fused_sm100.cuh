@@ -360,6 +360,16 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int v = 0; v < n_vis; ++v) {
         const int s = v & 1;
         const int q0 = q_block(v) * 128;
+        // row statistics of the query block: all eight loads of a lane in flight at once and before the ring wait (behind
+        // generic stores to shared memory ptxas keeps them in program order: four dependent round trips per visit)
+        float nl[4], nd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = q0 + lane * 4 + e;
+          const bool ok = r < p.N;
+          nl[e] = ok ? -__ldg(lsep + r) : -INFINITY;   // query rows past N: P = exp2(-inf) = 0
+          nd[e] = ok ? -__ldg(dlp + r) : 0.f;
+        }
         mbar_wait(&q_empty[s], ((v >> 1) & 1) ^ 1);          // Q_{v-2}, dO_{v-2} consumed (dK(v-2) is their last reader)
 #if FA_FUSED_TMA
         if (lane == 0) {
@@ -382,14 +392,9 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
 #endif
-        float* st = sStat + s * Cfg::kStatFloats;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = lane * 4 + e;
-          const bool ok = q0 + r < p.N;
-          st[r] = ok ? -lsep[q0 + r] : -INFINITY;  // query rows past N: P = exp2(-inf) = 0
-          st[128 + r] = ok ? -dlp[q0 + r] : 0.f;
-        }
+        float4* st = reinterpret_cast<float4*>(sStat + s * Cfg::kStatFloats);
+        st[lane] = make_float4(nl[0], nl[1], nl[2], nl[3]);
+        st[32 + lane] = make_float4(nd[0], nd[1], nd[2], nd[3]);
         mbar_arrive(&stat_full[s]);
       }
     } else if (warp == 13) {
