@@ -403,8 +403,21 @@ __host__ __device__ constexpr bool bwd_ew_split() { return ((FA_BWD_EW_SPLIT_MAS
 #endif
 template <int kD>
 __host__ __device__ constexpr bool dq_ds_tmem() { return kD == 64 && FA_DQ_DS_TMEM != 0 && bwd_ew_split<kD>(); }
+// FA_DKDV_KV_TMEM (takes the place of the third slot: 2 x 128 + 128 + 64 columns): dK/dV kernel at D = 64 with K_j / V_j
+// copied once into TMEM (columns 384-447) as the A operands of the score products — TS instead of shared-memory-bound SS
+// products with N = 64 (32 clk per instruction instead of 48), as the dQ kernel does with Q_i / dO_i.  With the statistics
+// ring in place (tools/kernel_times.py, config 2, same box, profiles/r02_dkdv_d64_kv_tmem.txt): two slots 0.599 ms, three
+// slots 0.511, two slots + K / V in TMEM 0.497 — both remove about the same wait, the TS products also halve the kernel's
+// shared-memory operand traffic; all three do not fit (576 columns).  Bit-identical.
+#ifndef FA_DKDV_KV_TMEM
+#define FA_DKDV_KV_TMEM 1
+#endif
 template <int kD>
-__host__ __device__ constexpr bool bwd_slots3() { return kD == 64 && FA_BWD_SLOTS3 != 0 && bwd_ew_split<kD>(); }
+__host__ __device__ constexpr bool dkdv_kv_tmem() { return kD == 64 && FA_DKDV_KV_TMEM != 0 && bwd_ew_split<kD>(); }
+template <int kD>
+__host__ __device__ constexpr bool bwd_slots3() {
+  return kD == 64 && FA_BWD_SLOTS3 != 0 && bwd_ew_split<kD>() && !dkdv_kv_tmem<kD>();
+}
 
 // One 32-column chunk of a half (dK/dV kernel; thread = one TMEM lane).  Same arithmetic as bwd_elementwise_half.
 // tS / tDP: the chunk's 32 fp32 columns; the packed results go to the first 16 columns of the chunk's OWN score columns
@@ -531,6 +544,8 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr bool kSlots3 = bwd_slots3<kD>();
   constexpr int kSlots = kSlots3 ? 3 : 2;
   constexpr bool kTwoStage = FA_DKDV_TWO_STAGE != 0 && !kSplit && !kDrop;
+  constexpr bool kKvTmem = dkdv_kv_tmem<kD>();
+  constexpr uint32_t kTmemKA = 384, kTmemVA = 416;   // kKvTmem: K_j / V_j as packed TMEM A operands (32 columns each)
   // TMEM: two slots = halves a / b at S [0,128) and dP [128,256); three slots = [S half | dP half] at 0 / 128 / 256
   constexpr uint32_t kAccV = kSlots3 ? 384 : Cfg::kTmemAcc0, kAccK = kSlots3 ? 448 : Cfg::kTmemAcc1;
   auto slot_s = [](int slot) -> uint32_t { return kSlots3 ? slot * 128 : Cfg::kTmemS + slot * 64; };
@@ -550,6 +565,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ uint64_t in_full[NS], in_empty[NS], stat_full[NT], stat_empty[NT];
   __shared__ uint64_t sc_full[kSlots], p_full[kSlots];
   __shared__ uint64_t s_full[2];   // two-stage elementwise: the S^T MMAs of a half have completed
+  __shared__ uint64_t kv_tmem;     // kKvTmem: K_j / V_j are in TMEM
   __shared__ uint32_t tmem_base_s;
   // kAmask with a block summary: the query blocks with something visible for this key block, in order
   __shared__ uint16_t s_list[kAmask ? 512 : 2];
@@ -598,6 +614,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&p_full[t], kSplit ? 256 : 128);
     }
     for (int t = 0; t < 2; ++t) mbar_init(&s_full[t], 1);
+    mbar_init(&kv_tmem, 256);
     fence_mbar_init();
   }
   if (warp == 8 && lane == 0) {
@@ -685,13 +702,15 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         static_for<0, kD / 16>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
-          umma_ss_off<off, off>(dS, k_lo, bq, idesc_sc, k > 0);
+          if constexpr (kKvTmem) umma_ts_off<k * 8, off>(dS, tmem + kTmemKA, bq, idesc_sc, k > 0);
+          else umma_ss_off<off, off>(dS, k_lo, bq, idesc_sc, k > 0);
         });
         if constexpr (kTwoStage) tc_commit(&s_full[slot]);
         static_for<0, kD / 16>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
           constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
-          umma_ss_off<off, off>(dDP, v_lo, bdo, idesc_sc, k > 0);
+          if constexpr (kKvTmem) umma_ts_off<k * 8, off>(dDP, tmem + kTmemVA, bdo, idesc_sc, k > 0);
+          else umma_ss_off<off, off>(dDP, v_lo, bdo, idesc_sc, k > 0);
         });
         tc_commit(&sc_full[slot]);
       };
@@ -715,6 +734,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       };
 
       mbar_wait(&kv_full, 0);
+      if constexpr (kKvTmem) mbar_wait(&kv_tmem, 0);
       if constexpr (kSlots3) {
         // halves k = 2 * step + half rotate through slots k % 3; the scores run three halves ahead of the gradients
         const int n_half = 2 * n_loop;
@@ -792,6 +812,24 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int row = (warp & 3) * 32 + lane;   // key row inside the block == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sl2 = p.scale_log2;
+    if constexpr (kKvTmem) {
+      // stationary operands: warpgroup a moves K_j, warpgroup b moves V_j from the swizzled TMA tile into TMEM,
+      // row r -> lane r, elements (2c, 2c + 1) -> column c (the dQ kernel does the same with Q_i / dO_i)
+      mbar_wait(&kv_full, 0);
+      const uint32_t src = smem_u32(half == 0 ? sK : sV);
+      uint32_t v[32];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t a = src + sw128_offset(row, ch);
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v[ch * 4]), "=r"(v[ch * 4 + 1]), "=r"(v[ch * 4 + 2]), "=r"(v[ch * 4 + 3])
+                     : "r"(a));
+      }
+      tmem_st_x32(tmem + (half == 0 ? kTmemKA : kTmemVA) + lane_base, v);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&kv_tmem);
+    }
     if constexpr (kSplit) {
     const int cbase = (warp >> 2) * 32;       // my 32 columns of every half
     uint32_t drop_col = 0, drop_shift = 0;
