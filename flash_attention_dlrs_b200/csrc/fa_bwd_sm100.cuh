@@ -401,6 +401,17 @@ __host__ __device__ constexpr bool bwd_ew_split() { return ((FA_BWD_EW_SPLIT_MAS
 #ifndef FA_DQ_DS_TMEM
 #define FA_DQ_DS_TMEM 1
 #endif
+// FA_DQ_FULL_SCORE (dQ kernel at D = 128, experiment, off): the score products issued as full 128-column SS products (an
+// SS product with N = 128 runs at the tensor peak, so Q_i / dO_i need no TMEM copies) — that frees 128 TMEM columns, 64 of
+// which take the packed dS of the block: dQ += dS K_j becomes a TS product and the hand-over loses its st.shared +
+// fence.proxy.async (10 % of the elementwise warps' ncu samples at D = 128).  Bit-identical (all GPU tests green), but
+// 1.48-1.58 ms against 1.19-1.22 on config 3 (profiles/r02_dq_full_score.txt): with one 1024-clock score product per block
+// both warpgroups get their scores at the same moment and the tensor pipe has no other half to work on meanwhile.
+#ifndef FA_DQ_FULL_SCORE
+#define FA_DQ_FULL_SCORE 0
+#endif
+template <int kD>
+__host__ __device__ constexpr bool dq_full_score() { return kD == 128 && FA_DQ_FULL_SCORE != 0 && !bwd_ew_split<kD>(); }
 template <int kD>
 __host__ __device__ constexpr bool dq_ds_tmem() { return kD == 64 && FA_DQ_DS_TMEM != 0 && bwd_ew_split<kD>(); }
 // FA_DKDV_KV_TMEM (takes the place of the third slot: 2 x 128 + 128 + 64 columns): dK/dV kernel at D = 64 with K_j / V_j
@@ -1005,6 +1016,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   constexpr int NK = Cfg::kStagesK, NV = Cfg::kStagesV;
   constexpr bool kSplit = bwd_ew_split<kD>();
   constexpr bool kDsTmem = dq_ds_tmem<kD>();
+  constexpr bool kFullScore = dq_full_score<kD>();
+  constexpr uint32_t kTmemDSFull = 384;   // kFullScore: packed dS, 32 columns per half
   constexpr int kPolyMask = kAmask ? 0 : (kD == 64 ? FA_BWD_POLY_MASK_D64 : FA_BWD_POLY_MASK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1120,7 +1133,27 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t k_mn = umma_lo_mnmajor(smem_u32(sK), Cfg::kBoxBytes);
 
       // S half = Q_i K_j[half]^T ; dP half = dO_i V_j[half]^T      (A operands resident in TMEM)
+      const uint32_t q_lo = umma_lo_kmajor(smem_u32(sQ)), do_lo = umma_lo_kmajor(smem_u32(sDO));
+      constexpr uint32_t idesc_full = umma_idesc_f16(kBf16, 128, 128, 0, 0);   // [128 q] x [128 kv], K = D
       auto issue_score = [&](int half, int sk, int sv) {
+        if constexpr (kFullScore) {
+          // both halves at once, operands from shared memory; each half's barrier is committed
+          if (half != 0) return;
+          const uint32_t bk = k_lo + sk * kTileLo, bv = v_lo + sv * kTileLo;
+          static_for<0, kD / 16>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+            umma_ss_off<off, off>(tmem + Cfg::kTmemS, q_lo, bk, idesc_full, k > 0);
+          });
+          static_for<0, kD / 16>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr uint32_t off = umma_koff_kmajor(k, Cfg::kBoxBytes);
+            umma_ss_off<off, off>(tmem + Cfg::kTmemDP, do_lo, bv, idesc_full, k > 0);
+          });
+          tc_commit(&sc_full[0]);
+          tc_commit(&sc_full[1]);
+          return;
+        }
         const uint32_t bk = k_lo + sk * kTileLo + half * kHalfLo, bv = v_lo + sv * kTileLo + half * kHalfLo;
         const uint32_t dS = tmem + Cfg::kTmemS + half * 64, dDP = tmem + Cfg::kTmemDP + half * 64;
         const uint32_t aQ = tmem + Cfg::kTmemQA, aDO = tmem + Cfg::kTmemDOA;
@@ -1147,6 +1180,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if constexpr (kDsTmem)
             umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dQ_t, tmem + Cfg::kTmemDS + half * 32, bk, idesc_gs,
                                                      !(first && k == 0));
+          else if constexpr (kFullScore)
+            umma_ts_off<k * 8, umma_koff_mnmajor(k)>(dQ_t, tmem + kTmemDSFull + half * 32, bk, idesc_gs,
+                                                     !(first && k == 0));
           else
             umma_ss_off<umma_koff_kmajor(k, Cfg::kBoxBytes), umma_koff_mnmajor(k)>(dQ_t, aDS, bk, idesc_gs,
                                                                                   !(first && k == 0));
@@ -1154,7 +1190,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_commit(&ds_free[half]);
       };
 
-      mbar_wait(&qdo_tmem, 0);
+      if constexpr (kFullScore) mbar_wait(&qdo_full, 0);
+      else mbar_wait(&qdo_tmem, 0);
       if (!kAmask || n_loop > 0) {
         mbar_wait(&k_full[0], 0);
         mbar_wait(&v_full[0], 0);
@@ -1171,6 +1208,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fa_trace(0, it, 0);
         if (more) {
           mbar_wait(&sc_free[0], it & 1);
+          if constexpr (kFullScore) mbar_wait(&sc_free[1], it & 1);
           mbar_wait(&k_full[skn], ((it + 1) / NK) & 1);
           mbar_wait(&v_full[svn], ((it + 1) / NV) & 1);
           tc_fence_after();
@@ -1227,7 +1265,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // Stationary operands: warpgroup a moves Q_i, warpgroup b moves dO_i from the (swizzled) TMA tile into TMEM,
     // row r -> lane r, elements (2c, 2c+1) -> column c.  As TMEM A operands they cost no shared-memory bandwidth
     // in the score MMAs (an SS MMA with N = 64 needs 192 B/clk of smem reads, above the 128 B/clk an SM has).
-    {
+    if constexpr (!kFullScore) {
       mbar_wait(&qdo_full, 0);
       const uint32_t src = smem_u32(half == 0 ? sQ : sDO);
       const uint32_t dstA = tmem + (half == 0 ? Cfg::kTmemQA : Cfg::kTmemDOA) + lane_base;
@@ -1355,13 +1393,20 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       else
         dq_elementwise_half<kBf16, false, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
                                                          drop_shift, p.drop.thresh, p.drop.rp, mk);
-      if (k > 0) mbar_wait(&ds_free[half], (k - 1) & 1);          // dQ MMAs of the previous block have read the box
+      if (k > 0) mbar_wait(&ds_free[half], (k - 1) & 1);          // dQ MMAs of the previous block have read dS
+      if constexpr (kFullScore) {
+        tc_fence_after();
+        tmem_st_x32(tmem + kTmemDSFull + half * 32 + lane_base, pd);
+        tc_wait_st();
+        tc_fence_before();
+      } else {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, ch)), "r"(pd[ch * 4]),
-                     "r"(pd[ch * 4 + 1]), "r"(pd[ch * 4 + 2]), "r"(pd[ch * 4 + 3])
-                     : "memory");
-      fence_proxy_async_smem();
+        for (int ch = 0; ch < 8; ++ch)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sds + sw128_offset(row, ch)), "r"(pd[ch * 4]),
+                       "r"(pd[ch * 4 + 1]), "r"(pd[ch * 4 + 2]), "r"(pd[ch * 4 + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+      }
       mbar_arrive(&p_full[half]);
       if (threadIdx.x == half * 128) fa_trace(1 + half, it, 2);   // dS handed over
     }
