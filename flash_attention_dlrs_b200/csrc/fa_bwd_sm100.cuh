@@ -19,7 +19,11 @@
 //   [grad a](t)  [score a](t+1)  [grad b](t)  [score b](t+1)
 // so the tensor core works on one half while the other half is in the elementwise stage.
 //
-//   warps 0-7  elementwise (P, dS) + epilogue      warp 8  TMA producer (+ row statistics)     warp 9  MMA issuer
+//   warps 0-7  elementwise (P, dS) + epilogue      warp 8  TMA producer      warp 9  MMA issuer
+//   warp 10    dK/dV kernel: row statistics (-lse, -delta) of the query blocks, a ring of their own filled blocks ahead
+// D = 64 variations (all bit-identical to the plain form): split elementwise stage (FA_BWD_EW_SPLIT_MASK), K_j / V_j as
+// TMEM A operands of the dK/dV kernel's score products (FA_DKDV_KV_TMEM) or three rotating score slots (FA_BWD_SLOTS3),
+// dS handed over through TMEM in the dQ kernel (FA_DQ_DS_TMEM).
 #pragma once
 
 #include "fa_dropout.cuh"
