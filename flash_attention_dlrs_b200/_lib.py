@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = (
     "fa_bwd_workspace_bytes",
     "fa_bwd",
     "fa_bwd_partial",
+    "fa_fwd_rect",
+    "fa_bwd_rect",
     "fa_merge_partial",
     "fa_accumulate",
     "fa_round_rows",
@@ -194,6 +196,15 @@ def _declare(lib):
                                    i, vp, f, ctypes.c_uint64, ctypes.POINTER(AttnMaskStruct), vp]
 
 
+def _declare_rect(lib):
+    vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    st = ctypes.POINTER(ctypes.c_int64)
+    lib.fa_fwd_rect.restype = i
+    lib.fa_fwd_rect.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, st, st, st, st, i, f, vp]
+    lib.fa_bwd_rect.restype = i
+    lib.fa_bwd_rect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, st, st, st, st, st, st, st, i, f, vp]
+
+
 def _declare_ring(lib):
     vp, i, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
     lib.fa_merge_partial.restype = i
@@ -224,6 +235,7 @@ def load():
                 if not hasattr(lib, sym):
                     raise FlashAttentionLibraryError(f"{LIB_PATH} does not export {sym}")
             _declare(lib)
+            _declare_rect(lib)
             _declare_ring(lib)
             _lib = lib
     return _lib

@@ -325,3 +325,42 @@ def backward(Q, K, V, O, dO, L, causal: bool, softmax_scale: float, which: int |
     if d_run != d:
         dQ, dK, dV = dQ[..., :d], dK[..., :d], dV[..., :d]
     return dQ, dK, dV
+
+
+def forward_rect(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, softmax_scale: float):
+    """Rectangular attention: Q (B,H,Nq,d) against K, V (B,H,Nk,d), Nk != Nq allowed (fa_fwd_rect: float16 / bfloat16,
+    d in {64, 128}, non-causal).  Returns O (B,H,Nq,d) and L (B,H,Nq) float32 in log2 units."""
+    lib = _lib.load()
+    B, H, Nq, d = Q.shape
+    Nk = K.shape[2]
+    if K.shape != V.shape or K.shape[:2] != Q.shape[:2] or K.shape[3] != d:
+        raise ValueError("forward_rect: Q (B,H,Nq,d), K and V (B,H,Nk,d)")
+    q, k, v = (_kernel_ready(t) for t in (Q, K, V))
+    O = torch.empty((B, H, Nq, d), dtype=Q.dtype, device=Q.device)
+    L = torch.empty((B, H, Nq), dtype=torch.float32, device=Q.device)
+    with _on_device(Q.device):
+        rc = lib.fa_fwd_rect(_ptr(q), _ptr(k), _ptr(v), _ptr(O), _ptr(L), B, H, Nq, Nk, d, _lib.strides4(q),
+                             _lib.strides4(k), _lib.strides4(v), _lib.strides4(O), dtype_code(Q.dtype),
+                             float(softmax_scale), _stream_ptr(Q.device))
+    _lib.check(rc, "fa_fwd_rect")
+    return O, L
+
+
+def backward_rect(Q, K, V, O, dO, L, softmax_scale: float, delta=None):
+    """Gradients of forward_rect: dQ (B,H,Nq,d), dK, dV (B,H,Nk,d); deterministic (the two-kernel path)."""
+    lib = _lib.load()
+    B, H, Nq, d = Q.shape
+    Nk = K.shape[2]
+    q, k, v, o, do = (_kernel_ready(t) for t in (Q, K, V, O, dO))
+    lse = L if (L.dtype == torch.float32 and L.is_contiguous()) else L.to(torch.float32).contiguous()
+    if delta is None:
+        delta = backward_preprocess(o, do)
+    dQ = torch.empty((B, H, Nq, d), dtype=Q.dtype, device=Q.device)
+    dK, dV = (torch.empty((B, H, Nk, d), dtype=Q.dtype, device=Q.device) for _ in range(2))
+    with _on_device(Q.device):
+        rc = lib.fa_bwd_rect(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(lse), _ptr(delta), _ptr(dQ), _ptr(dK), _ptr(dV),
+                             B, H, Nq, Nk, d, _lib.strides4(q), _lib.strides4(k), _lib.strides4(v), _lib.strides4(do),
+                             _lib.strides4(dQ), _lib.strides4(dK), _lib.strides4(dV), dtype_code(Q.dtype),
+                             float(softmax_scale), _stream_ptr(Q.device))
+    _lib.check(rc, "fa_bwd_rect")
+    return dQ, dK, dV

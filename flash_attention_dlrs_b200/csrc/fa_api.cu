@@ -205,7 +205,7 @@ extern "C" int fa_debug_set_trace(void* dev_buf, int capacity_events) {
 
 extern "C" {
 
-int fa_version(void) { return 8; }
+int fa_version(void) { return 9; }
 
 const char* fa_last_error(void) { return g_err; }
 
@@ -216,12 +216,48 @@ int fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int
                       causal, 0, nullptr, nullptr, 0.f, 0, nullptr, stream);
 }
 
+// Rectangular problems (Nk key / value rows != N query rows): 16-bit tcgen05 kernels, non-causal, no seqlens / dropout / mask.
+static int check_rect(const char* fn, int N, int Nk, int dtype, int causal, const int32_t* seqlens, float dropout_p,
+                      const fa_attn_mask* mask) {
+  if (Nk == N) return 0;
+  if (Nk <= 0) return fail(-1, "%s: Nk must be positive (got %d)", fn, Nk);
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16)
+    return fail(-2, "%s: a key length different from the query length needs float16 / bfloat16 (dtype %d)", fn, dtype);
+  if (causal) return fail(-15, "%s: the causal mask needs Nk == N (got %d, %d)", fn, Nk, N);
+  if (seqlens || mask || dropout_p != 0.f)
+    return fail(-15, "%s: seqlens, dropout and attention masks need Nk == N", fn);
+  return 0;
+}
+
+static int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int Nk, int D,
+                    const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+                    const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
+                    void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                    const fa_attn_mask* mask, void* stream);
+
 int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int D,
                  const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
                  const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
                  void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
                  const fa_attn_mask* mask, void* stream) {
+  return fwd_impl(q, k, v, o, lse, B, H, N, N, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale, causal,
+                  n_peers, peer_o, seqlens, dropout_p, dropout_seed, mask, stream);
+}
+
+int fa_fwd_rect(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq, int Nk, int D,
+                const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+                const int64_t o_strides[4], int dtype, float softmax_scale, void* stream) {
+  return fwd_impl(q, k, v, o, lse, B, H, Nq, Nk, D, q_strides, k_strides, v_strides, o_strides, dtype, softmax_scale, 0, 0,
+                  nullptr, nullptr, 0.f, 0, nullptr, stream);
+}
+
+static int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int Nk, int D,
+                    const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+                    const int64_t o_strides[4], int dtype, float softmax_scale, int causal, int n_peers,
+                    void* const* peer_o, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                    const fa_attn_mask* mask, void* stream) {
   g_err[0] = 0;
+  if (int r = check_rect("fa_fwd", N, Nk, dtype, causal, seqlens, dropout_p, mask)) return r;
   const uint8_t* attn_mask = mask ? mask->rows : nullptr;
   const int64_t* attn_mask_strides = mask ? mask->rows_strides : nullptr;
   if (int r = check_amask("fa_fwd_peers", "attn_mask->rows", attn_mask, attn_mask_strides, N)) return r;
@@ -273,14 +309,15 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   const int bf = dtype == FA_DTYPE_BF16;
   const bool f8 = dtype == FA_DTYPE_F8E4M3 || dtype == FA_DTYPE_F8E5M2;
   CUtensorMap tq, tk, tv;
-  auto encode = [&](CUtensorMap* m, const void* ptr, const int64_t* st4) {
-    return fa::cached_tmap_bhnd(m, ptr, f8 ? 2 : bf, B, H, N, D, st4[0], st4[1], st4[2], 128);
+  auto encode = [&](CUtensorMap* m, const void* ptr, const int64_t* st4, int rows) {
+    return fa::cached_tmap_bhnd(m, ptr, f8 ? 2 : bf, B, H, rows, D, st4[0], st4[1], st4[2], 128);
   };
-  if (int r = encode(&tq, q, q_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
-  if (int r = encode(&tk, k, k_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
-  if (int r = encode(&tv, v, v_strides)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
+  if (int r = encode(&tq, q, q_strides, N)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
+  if (int r = encode(&tk, k, k_strides, Nk)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
+  if (int r = encode(&tv, v, v_strides, Nk)) return fail(r, "fa_fwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
   fa::FwdParams p{};
   p.o = o, p.lse = lse, p.B = B, p.H = H, p.N = N;
+  p.Nk = Nk != N ? Nk : 0;
   p.o_sB = o_strides[0], p.o_sH = o_strides[1], p.o_sN = o_strides[2];
   p.scale_log2 = softmax_scale * kLog2e;
   p.q_blocks = (N + 255) / 256;
@@ -293,7 +330,7 @@ int fa_fwd_peers(const void* q, const void* k, const void* v, void* o, float* ls
   if (band) p.band = 1, p.win_left = mask->window_left, p.win_right = mask->window_right;
   if (mask && mask->blocks)
     p.ablock = mask->blocks, p.ab_sB = mask->blocks_strides[0], p.ab_sH = mask->blocks_strides[1], p.ab_sI = mask->blocks_strides[2];
-  if (fa_host::fwd_pair_eligible(dtype, D, p)) {
+  if (Nk == N && fa_host::fwd_pair_eligible(dtype, D, p)) {
     CUtensorMap tk64;
     if (int r = fa::cached_tmap_bhnd(&tk64, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 64))
       return fail(r, "fa_fwd: cuTensorMapEncodeTiled(k, 64-row box) failed (%d)", r);
@@ -360,6 +397,14 @@ int fa_bwd(const void* q, const void* k, const void* v, const void* dout, const 
                         causal, FA_BWD_DKDV | FA_BWD_DQ, nullptr, 0.f, 0, nullptr, stream);
 }
 
+static int bwd_impl(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                    const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+                    int H, int N, int Nk, int D, const int64_t q_strides[4], const int64_t k_strides[4],
+                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
+                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
+                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                    const fa_attn_mask* mask, void* stream);
+
 int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout, const float* lse,
                    const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
                    int H, int N, int D, const int64_t q_strides[4], const int64_t k_strides[4],
@@ -367,7 +412,31 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
                    const fa_attn_mask* mask, void* stream) {
+  return bwd_impl(q, k, v, dout, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, H, N, N, D, q_strides, k_strides,
+                  v_strides, do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale, causal, which, seqlens,
+                  dropout_p, dropout_seed, mask, stream);
+}
+
+int fa_bwd_rect(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+                void* dq, void* dk, void* dv, int B, int H, int Nq, int Nk, int D, const int64_t q_strides[4],
+                const int64_t k_strides[4], const int64_t v_strides[4], const int64_t do_strides[4],
+                const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype,
+                float softmax_scale, void* stream) {
+  return bwd_impl(q, k, v, dout, lse, delta, dq, dk, dv, nullptr, 0, B, H, Nq, Nk, D, q_strides, k_strides, v_strides,
+                  do_strides, dq_strides, dk_strides, dv_strides, dtype, softmax_scale, 0, FA_BWD_DKDV | FA_BWD_DQ, nullptr,
+                  0.f, 0, nullptr, stream);
+}
+
+static int bwd_impl(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                    const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+                    int H, int N, int Nk, int D, const int64_t q_strides[4], const int64_t k_strides[4],
+                    const int64_t v_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
+                    const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, float softmax_scale,
+                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
+                    const fa_attn_mask* mask, void* stream) {
   g_err[0] = 0;
+  if (int r = check_rect("fa_bwd", N, Nk, dtype, causal, seqlens, dropout_p, mask)) return r;
+  if (Nk != N && which == FA_BWD_FUSED) return fail(-15, "fa_bwd: FA_BWD_FUSED needs Nk == N");
   const uint8_t* attn_mask = mask ? mask->rows : nullptr;
   const uint8_t* attn_mask_t = mask ? mask->cols : nullptr;
   const int64_t* attn_mask_strides = mask ? mask->rows_strides : nullptr;
@@ -439,15 +508,16 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
   fa::BwdMaps m;
   if (int r = fa::cached_tmap_bhnd(&m.q, q, bf, B, H, N, D, q_strides[0], q_strides[1], q_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(q) failed (%d)", r);
-  if (int r = fa::cached_tmap_bhnd(&m.k, k, bf, B, H, N, D, k_strides[0], k_strides[1], k_strides[2], 128))
+  if (int r = fa::cached_tmap_bhnd(&m.k, k, bf, B, H, Nk, D, k_strides[0], k_strides[1], k_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(k) failed (%d)", r);
-  if (int r = fa::cached_tmap_bhnd(&m.v, v, bf, B, H, N, D, v_strides[0], v_strides[1], v_strides[2], 128))
+  if (int r = fa::cached_tmap_bhnd(&m.v, v, bf, B, H, Nk, D, v_strides[0], v_strides[1], v_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(v) failed (%d)", r);
   if (int r = fa::cached_tmap_bhnd(&m.dout, dout, bf, B, H, N, D, do_strides[0], do_strides[1], do_strides[2], 128))
     return fail(r, "fa_bwd: cuTensorMapEncodeTiled(dout) failed (%d)", r);
   fa::BwdParams p{};
   p.lse = lse, p.delta = delta, p.dq = dq, p.dk = dk, p.dv = dv;
   p.B = B, p.H = H, p.N = N;
+  p.Nk = Nk != N ? Nk : 0;
   fill3(p.dq_s, dq_strides), fill3(p.dk_s, dk_strides), fill3(p.dv_s, dv_strides);
   p.scale = softmax_scale, p.scale_log2 = softmax_scale * kLog2e;
   p.seqlens = seqlens;

@@ -52,6 +52,7 @@ struct BwdParams {
   const float* delta;  // (B,H,N)
   void *dq, *dk, *dv;  // (B,H,N,D) 16-bit
   int B, H, N;
+  int Nk;              // key / value rows when they differ from the N query rows (rectangular attention); 0 = N
   int64_t dq_s[3], dk_s[3], dv_s[3];  // {sB,sH,sN}
   float scale, scale_log2;
   const int* seqlens;  // per-batch valid length (key-padding mask), nullptr = N; see FwdParams::seqlens
@@ -590,8 +591,9 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = jb * 128;
-  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
-  if (k0 >= nv) return;   // padded key block: dK / dV rows stay as the caller initialised them
+  const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element (queries)
+  const int nk = p.Nk > 0 ? p.Nk : nv;                               // valid key rows
+  if (k0 >= nk) return;   // padded key block: dK / dV rows stay as the caller initialised them
   // Padded keys inside the last block need no mask here: rows = keys, and a padded key only feeds its own dK / dV rows,
   // which are never stored.  Padded queries get -L = -inf below, i.e. P = 0.
   const int n_q_total = (nv + 127) >> 7;
@@ -994,7 +996,7 @@ fa_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const int kv_row = k0 + row;
-    const bool in_range = kv_row < nv;
+    const bool in_range = kv_row < nk;
     if (half == 0) {
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.dv) + b * p.dv_s[0] + h * p.dv_s[1] + (int64_t)kv_row * p.dv_s[2];
       store_acc_rows<kBf16>(tmem + kAccV + lane_base, kD, kDrop ? p.drop.rp : 1.0f, dst, in_range,
@@ -1046,11 +1048,12 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int q0 = ib * 128;
   const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
   if (q0 >= nv) return;   // padded query block
-  const int n_kv_valid = (nv + 127) >> 7;
+  const int nk = p.Nk > 0 ? p.Nk : nv;   // valid key rows
+  const int n_kv_valid = (nk + 127) >> 7;
   const int n_it = kCausal ? ib + 1 : n_kv_valid;
   // Non-causal: keys >= nv in the last key block are masked explicitly (padded K rows are real data, not TMA zero fill);
   // causal: the diagonal mask of the last block already removes them (valid rows are < nv).
-  const bool tail_mask = !kCausal && (nv & 127) != 0;
+  const bool tail_mask = !kCausal && (nk & 127) != 0;
   const bool use_list = kAmask && p.ablock != nullptr && n_it <= 512;
   if constexpr (kAmask) {
     if (use_list && warp == 0) {   // one warp compacts the flags (ballot + prefix count), 32 blocks per step
@@ -1323,7 +1326,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             dq_elementwise_chunk<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd,
                                                                                dw, drop_shift, p.drop.thresh, p.drop.rp, mkw, band_lo, band_hi);
           else if (tail_mask && it == n_it - 1)
-            dq_elementwise_chunk<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, nv - it * 128 - 1,
+            dq_elementwise_chunk<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, nk - it * 128 - 1,
                                                                                hf * 64, cbase, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mkw,
                                                                                band_lo, band_hi);
           else
@@ -1333,7 +1336,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           dq_elementwise_chunk<kBf16, true, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd, dw,
                                                                             drop_shift, p.drop.thresh, p.drop.rp, mkw, 0, 0);
         else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
-          dq_elementwise_chunk<kBf16, true, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, nv - it * 128 - 1,
+          dq_elementwise_chunk<kBf16, true, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, nk - it * 128 - 1,
                                                                             hf * 64, cbase, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mkw, 0, 0);
         else
           dq_elementwise_chunk<kBf16, false, kDrop, kAmask, false, kPolyMask>(tSc, tDPc, &sc_free[hf], nl2, nd2, sl2, row, hf * 64, cbase, pd, dw,
@@ -1382,7 +1385,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd,
                                                                   dw, drop_shift, p.drop.thresh, p.drop.rp, mk, band_lo, band_hi);
         else if (tail_mask && it == n_it - 1)
-          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
+          dq_elementwise_half<kBf16, true, kDrop, kAmask, kAmask, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nk - it * 128 - 1,
                                                                   half * 64, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mk,
                                                                   band_lo, band_hi);
         else
@@ -1392,7 +1395,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         dq_elementwise_half<kBf16, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,
                                                         drop_shift, p.drop.thresh, p.drop.rp, mk);
       else if (tail_mask && it == n_it - 1)   // last key block: keep key < nv
-        dq_elementwise_half<kBf16, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nv - it * 128 - 1,
+        dq_elementwise_half<kBf16, true, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, nk - it * 128 - 1,
                                                         half * 64, pd, dw, drop_shift, p.drop.thresh, p.drop.rp, mk);
       else
         dq_elementwise_half<kBf16, false, kDrop, kAmask, false, kPolyMask>(tS, tDP, &sc_free[half], nl2, nd2, sl2, row, half * 64, pd, dw,

@@ -43,6 +43,7 @@ struct FwdParams {
   void* o;       // (B,H,N,D) 16-bit
   float* lse;    // (B,H,N) fp32, log2 units
   int B, H, N;
+  int Nk;   // key / value rows when they differ from the N query rows (rectangular attention: non-causal, no seqlens / masks); 0 = N
   int64_t o_sB, o_sH, o_sN;  // element strides of O (last dim contiguous)
   float scale_log2;          // softmax_scale * log2(e)
   int q_blocks;              // ceil(N / 256)
@@ -128,7 +129,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int q0 = qb * 256;
   const int nv = p.seqlens ? min(max(p.seqlens[b], 0), p.N) : p.N;   // valid length of this batch element
   if (q0 >= nv) return;                                              // whole CTA is padding (uniform, before any set-up)
-  const int n_kv_total = (nv + 127) >> 7;
+  const int nk = p.Nk > 0 ? p.Nk : nv;                               // valid key rows
+  const int n_kv_total = (nk + 127) >> 7;
   const int ntiles = (nv - q0 > 128) ? 2 : 1;
   int nkv[2];
 #pragma unroll
@@ -359,10 +361,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
       const int kv0 = j * 128;
       const bool diag = kCausal && (kv0 + 127 > q0 + 128 * t);   // block touches the diagonal
-      const bool ragged = (kv0 + 128 > nv);
+      const bool ragged = (kv0 + 128 > nk);
       const bool band_cut = kAmask && partial && !am_row;   // band mask (no bytes): the band's edge crosses this block
       if (diag || ragged || band_cut) {
-        int limit = nv - kv0;                          // first invalid column (ragged / padded keys)
+        int limit = nk - kv0;                          // first invalid column (ragged / padded keys)
         if (kCausal) limit = min(limit, q_row - kv0 + 1);
         int lo = 0;                                    // first visible column (band masks only)
         if constexpr (kAmask) {

@@ -26,7 +26,7 @@ int launch(const fa::BwdMaps& m, const fa::BwdParams& p, cudaStream_t st) {
   auto kern = fa::fa_bwd_dkdv_kernel<kBf16, kD, kCausal, kDrop, kAmask>;
   static std::atomic<uint64_t> smem_set{0};   // per instantiation: devices whose attribute is set
   if (int r = fa_host::set_smem_once(kern, fa::BwdCfg<kD>::kSmemDkdv, smem_set)) return r;
-  dim3 grid((p.N + 127) / 128, p.H, p.B);
+  dim3 grid(((p.Nk > 0 ? p.Nk : p.N) + 127) / 128, p.H, p.B);   // one CTA per key block
   kern<<<grid, fa::BwdCfg<kD>::kThreads, fa::BwdCfg<kD>::kSmemDkdv, st>>>(m.q, m.k, m.v, m.dout, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fa_host::cuda_fail(e, "fa_bwd(dK/dV) launch");

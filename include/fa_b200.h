@@ -135,6 +135,20 @@ int fa_bwd_partial(const void* q, const void* k, const void* v, const void* dout
                    int causal, int which, const int32_t* seqlens, float dropout_p, uint64_t dropout_seed,
                    const fa_attn_mask* attn_mask, void* stream);
 
+/* Rectangular attention: Nq query rows against Nk key / value rows (Nk != Nq allowed) — cross-attention, and the step of the
+ * sequence-parallel path in which one query chunk meets a whole visiting key / value shard (or a whole query shard one key
+ * chunk).  The same kernels as fa_fwd / fa_bwd with the key loops bounded by Nk; float16 / bfloat16, D in {64, 128},
+ * non-causal, no seqlens / dropout / mask.  o, dq: (B, H, Nq, D); k, v, dk, dv: (B, H, Nk, D); lse, delta: (B, H, Nq).
+ * The reference has square problems only (flash_attention_torch.py:27-32 requires equal shapes). */
+int fa_fwd_rect(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq, int Nk, int D,
+                const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+                const int64_t o_strides[4], int dtype, float softmax_scale, void* stream);
+int fa_bwd_rect(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+                void* dq, void* dk, void* dv, int B, int H, int Nq, int Nk, int D, const int64_t q_strides[4],
+                const int64_t k_strides[4], const int64_t v_strides[4], const int64_t do_strides[4],
+                const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype,
+                float softmax_scale, void* stream);
+
 /* Sequence-parallel (ring) attention helpers — no counterpart in the reference (single GPU); they sit where a caller that
  * shards the SEQUENCE across GPUs combines what fa_fwd / fa_bwd return for one key / value shard at a time.
  * All buffers contiguous; 16-bit partials (dtype 0 / 1), fp32 accumulators.

@@ -285,6 +285,41 @@ def test_cpp_autograd_node_is_bitwise_the_python_function(dtype, D, N, causal, m
     assert not node.supported(Qp, Qp, Qp) and FlashAttention.apply(Qp, Qp, Qp).shape == Qp.shape
 
 
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 128), (torch.float16, 64)])
+@pytest.mark.parametrize("Nq,Nk", [(256, 512), (512, 256), (200, 333), (1, 130), (384, 128)])
+def test_rectangular_attention_matches_the_oracle(dtype, D, Nq, Nk):
+    """fa_fwd_rect / fa_bwd_rect: Nq query rows against Nk key rows (the ring path's one-chunk-against-a-shard step, and
+    cross-attention) against the fp64 closed form; Nk == Nq must reproduce the square entry points bit for bit."""
+    B, H, scale = 2, 3, 1.0 / math.sqrt(D)
+    g = torch.Generator().manual_seed(5)
+    Q, dO = (torch.randn(B, H, Nq, D, generator=g).to(dtype).to(DEV) for _ in range(2))
+    K, V = (torch.randn(B, H, Nk, D, generator=g).to(dtype).to(DEV) for _ in range(2))
+    O, L = _native.forward_rect(Q, K, V, scale)
+    dQ, dK, dV = _native.backward_rect(Q, K, V, O, dO, L, scale)
+    q, k, v, do = (t.cpu().double() for t in (Q, K, V, dO))
+    q.requires_grad_(True), k.requires_grad_(True), v.requires_grad_(True)
+    S = (q @ k.transpose(-1, -2)) * scale
+    ref_O = torch.softmax(S, -1) @ v
+    ref_L = torch.logsumexp(S, -1) * math.log2(math.e)
+    gq, gk, gv = torch.autograd.grad(ref_O, (q, k, v), do)
+    assert (L.cpu().double() - ref_L).abs().max() <= 2e-3
+    assert (O.cpu().double() - ref_O).abs().max() <= 2e-3 + 2.0 ** -8 * ref_O.abs().max()
+    for name, got, ref in (("dQ", dQ, gq), ("dK", dK, gk), ("dV", dV, gv)):
+        assert rel_err(got.cpu(), ref) <= 1e-2, name
+    # square problems through the rectangular entry points are the square kernels
+    K2, V2 = (torch.randn(B, H, Nq, D, generator=g).to(dtype).to(DEV) for _ in range(2))
+    O2, L2 = _native.forward_rect(Q, K2, V2, scale)
+    O3, L3 = _native.forward(Q, K2, V2, False, scale)
+    assert torch.equal(O2, O3) and torch.equal(L2, L3)
+    for a, b in zip(_native.backward_rect(Q, K2, V2, O2, dO, L2, scale), _native.backward(Q, K2, V2, O3, dO, L3, False, scale)):
+        assert torch.equal(a, b)
+    # what the rectangular path does not take
+    lib = _lib.load()
+    s4 = _lib.strides4(Q)
+    assert lib.fa_fwd_rect(_native._ptr(Q), _native._ptr(K), _native._ptr(V), _native._ptr(O), _native._ptr(L), B, H, Nq, 0, D,
+                           s4, _lib.strides4(K), _lib.strides4(V), s4, _native.dtype_code(dtype), scale, None) < 0
+
+
 def test_preprocess_parity():
     for dtype, D in ((torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)):
         O, dO = (torch.randn(2, 5, 300, D, device=DEV).to(dtype) for _ in range(2))
