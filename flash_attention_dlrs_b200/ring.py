@@ -36,7 +36,7 @@ class CudaOps:
 
     @staticmethod
     def fwd(q, k, v, causal, scale):
-        if q.shape[2] != k.shape[2]:      # one query chunk against a whole visiting shard, or the reverse (never causal)
+        if q.shape[2] != k.shape[2]:      # rectangular partial (fa_fwd_rect; never causal)
             return _native.forward_rect(q, k, v, scale)
         return _native.forward(q, k, v, causal, scale)            # O (B,H,n,D) 16-bit, L (B,H,n) fp32 (log2 units)
 
@@ -321,42 +321,6 @@ def _relation(causal: bool, q_id: int, k_id: int):
     return None if k_id > q_id else (k_id == q_id)
 
 
-def _launches(causal: bool, q_blocks, k_blocks):
-    """The block products of one ring step, grouped into kernel launches:
-    [(q_slice, k_slice, causal_kernel, [(qi, row offset in the launch, rows)], [(ki, row offset, rows)])].
-    Unmasked products that share their key chunk and cover both (adjacent) query chunks of the shard run as ONE launch over the
-    whole query shard, and likewise one query chunk against both key chunks of the visiting shard (rectangular problems,
-    fa_fwd_rect / fa_bwd_rect): under the zigzag causal schedule every step after the first is then a single launch instead
-    of two half-size ones (a non-causal zigzag step one instead of four), with half as many merges and CTAs that run twice
-    as long.  Diagonal (causal-kernel) products stay on their own."""
-    rel = {(qi, ki): _relation(causal, q_id, k_id) for qi, (_, q_id) in enumerate(q_blocks)
-           for ki, (_, k_id) in enumerate(k_blocks)}
-    nq, nk = len(q_blocks), len(k_blocks)
-    span = lambda blocks: slice(blocks[0][0].start, blocks[-1][0].stop)
-    parts = lambda blocks, idx: [(i, blocks[i][0].start - blocks[idx[0]][0].start, blocks[i][0].stop - blocks[i][0].start)
-                                 for i in idx]
-    out, used = [], set()
-    free = lambda qi, ki: rel[(qi, ki)] is False and (qi, ki) not in used
-    if nq == 2 and nk == 2 and all(rel[(qi, ki)] is False for qi in range(2) for ki in range(2)):
-        used.update(rel)
-        out.append((span(q_blocks), span(k_blocks), False, parts(q_blocks, [0, 1]), parts(k_blocks, [0, 1])))
-    if nq == 2:
-        for ki in range(nk):
-            if free(0, ki) and free(1, ki):
-                used.update({(0, ki), (1, ki)})
-                out.append((span(q_blocks), k_blocks[ki][0], False, parts(q_blocks, [0, 1]), parts(k_blocks, [ki])))
-    if nk == 2:
-        for qi in range(nq):
-            if free(qi, 0) and free(qi, 1):
-                used.update({(qi, 0), (qi, 1)})
-                out.append((q_blocks[qi][0], span(k_blocks), False, parts(q_blocks, [qi]), parts(k_blocks, [0, 1])))
-    for qi in range(nq):
-        for ki in range(nk):
-            if rel[(qi, ki)] is not None and (qi, ki) not in used:
-                out.append((q_blocks[qi][0], k_blocks[ki][0], rel[(qi, ki)], parts(q_blocks, [qi]), parts(k_blocks, [ki])))
-    return out
-
-
 def ring_attention_forward(Q, K, V, causal: bool = False, softmax_scale: float = 1.0, group=None, ops=CudaOps,
                            zigzag: bool = False, transport=None):
     """Local shards in, (O_local in the input dtype, L_local (B,H,n,1) float32 in log2 units) out.
@@ -374,11 +338,13 @@ def ring_attention_forward(Q, K, V, causal: bool = False, softmax_scale: float =
     for s in range(G):
         c = (r - s) % G                       # rank whose K / V shard is visiting at step s
         tr.prefetch_kv(s)                     # NCCL: next step's K / V are in flight while this step computes
-        for qs, ks, rel, q_parts, _ in _launches(causal, q_blocks, _blocks(c, G, n, zigzag)):
-            o_part, l_part = ops.fwd(Q[:, :, qs], kv[0][:, :, ks], kv[1][:, :, ks], rel, float(softmax_scale))
-            l_part = l_part.reshape(B, H, qs.stop - qs.start)
-            for qi, off, rows in q_parts:
-                ops.merge(o_acc[qi], l_acc[qi], o_part[:, :, off:off + rows], l_part[:, :, off:off + rows], first[qi])
+        for qi, (qs, q_id) in enumerate(q_blocks):
+            for ks, k_id in _blocks(c, G, n, zigzag):
+                rel = _relation(causal, q_id, k_id)
+                if rel is None:
+                    continue
+                o_part, l_part = ops.fwd(Q[:, :, qs], kv[0][:, :, ks], kv[1][:, :, ks], rel, float(softmax_scale))
+                ops.merge(o_acc[qi], l_acc[qi], o_part, l_part.reshape(l_acc[qi].shape), first[qi])
                 first[qi] = False
         if s + 1 < G:
             kv = tr.next_kv(s)
@@ -415,26 +381,22 @@ def ring_attention_backward(Q, K, V, O, dO, L, causal: bool = False, softmax_sca
             else:
                 dkv_acc = tr.recv_acc(s)      # sums of shard c so far, arriving with it from rank r-1
         parts = []
-        for qs, ks, rel, q_parts, k_parts in _launches(causal, q_blocks, _blocks(c, G, n, zigzag)):
-            one = len(q_parts) == 1
-            Lq = Lb[q_parts[0][0]] if one else L3[:, :, qs].contiguous()
-            dq = db[q_parts[0][0]] if one else delta[:, :, qs].contiguous()
-            dq_p, dk_p, dv_p = ops.bwd(Q[:, :, qs], kv[0][:, :, ks], kv[1][:, :, ks], O[:, :, qs], dO[:, :, qs], Lq, rel,
-                                       float(softmax_scale), dq)
-            # per chunk, in launch order: the same fixed order of additions on every run
-            parts.append(([(qi, dq_p[:, :, off:off + rows]) for qi, off, rows in q_parts],
-                          [(ki, dk_p[:, :, off:off + rows], dv_p[:, :, off:off + rows]) for ki, off, rows in k_parts]))
+        for qi, (qs, q_id) in enumerate(q_blocks):
+            for ki, (ks, k_id) in enumerate(_blocks(c, G, n, zigzag)):
+                rel = _relation(causal, q_id, k_id)
+                if rel is None:
+                    continue
+                parts.append((qi, ki) + tuple(ops.bwd(Q[:, :, qs], kv[0][:, :, ks], kv[1][:, :, ks], O[:, :, qs],
+                                                      dO[:, :, qs], Lb[qi], rel, float(softmax_scale), db[qi])))
         if s > 0 and overlap:
             dkv_acc = tr.recv_acc(s)
         touched = [s > 0] * nb                # at s = 0 the accumulators of the own shard start from nothing
-        for dq_parts, dkv_parts in parts:   # same order of additions as the kernels were launched in: deterministic
-            for qi, dq_p in dq_parts:
-                ops.accumulate(dq_acc[qi], dq_p, first_q[qi])
-                first_q[qi] = False
-            for ki, dk_p, dv_p in dkv_parts:
-                ops.accumulate(dkv_acc[2 * ki], dk_p, not touched[ki])
-                ops.accumulate(dkv_acc[2 * ki + 1], dv_p, not touched[ki])
-                touched[ki] = True
+        for qi, ki, dq_p, dk_p, dv_p in parts:   # same order of additions as the kernels were launched in: deterministic
+            ops.accumulate(dq_acc[qi], dq_p, first_q[qi])
+            first_q[qi] = False
+            ops.accumulate(dkv_acc[2 * ki], dk_p, not touched[ki])
+            ops.accumulate(dkv_acc[2 * ki + 1], dv_p, not touched[ki])
+            touched[ki] = True
         for ki in range(nb):                  # a chunk nobody on this rank attends to at s = 0 still needs defined sums
             if not touched[ki]:
                 dkv_acc[2 * ki].zero_(), dkv_acc[2 * ki + 1].zero_()
