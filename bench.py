@@ -324,9 +324,10 @@ def c4_strong(world, rank, dev, barrier):
         O, L = flash_attention_forward(Q, K, V, dev, True, scale)
         return O, flash_attention_backward(Q, K, V, O, dO, L, dev, True, True, scale)
 
-    step()
+    for _ in range(3):   # the same warm-up rule as the main measurement (this record follows a PCIe-bound phase: the
+        step()           # boards come out of it at idle power and take tens of ms to ramp — one warm step read 2x slow on 8 GPUs)
     barrier()
-    steps = 3
+    steps = 5
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
