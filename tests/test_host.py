@@ -307,3 +307,20 @@ def test_cpp_autograd_node_loads_and_declines_what_it_does_not_serve():
     with pytest.raises(NotImplementedError):
         fat.FlashAttention.apply(q, q, q)                   # ... raise like the reference, through the Python Function
     assert fat.FlashAttentionDeterministic.apply.__func__ is fat.FlashAttention.apply.__func__
+
+
+def test_rectangular_entry_points_reject_what_they_do_not_take():
+    """fa_fwd_rect / fa_bwd_rect (ABI v9): argument checks run before anything touches the GPU."""
+    lib = _lib.load()
+    s = (ctypes.c_int64 * 4)(64 * 128, 128 * 64, 64, 1)
+    null = ctypes.c_void_p(0)
+    # a key length of zero, float32 with Nk != Nq
+    assert lib.fa_fwd_rect(null, null, null, null, null, 1, 1, 128, 0, 64, s, s, s, s, 1, 1.0, null) < 0
+    assert b"Nk" in lib.fa_last_error()
+    assert lib.fa_fwd_rect(null, null, null, null, null, 1, 1, 128, 256, 64, s, s, s, s, 2, 1.0, null) < 0
+    assert b"float16 / bfloat16" in lib.fa_last_error()
+    # null tensors are refused like in fa_fwd
+    assert lib.fa_fwd_rect(null, null, null, null, null, 1, 1, 128, 256, 64, s, s, s, s, 1, 1.0, null) < 0
+    assert b"null" in lib.fa_last_error()
+    assert lib.fa_bwd_rect(null, null, null, null, null, null, null, null, null, 1, 1, 128, 256, 64, s, s, s, s, s, s, s, 1,
+                           1.0, null) < 0
